@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FlashAttention.jl hot path on B200.
+
+Workload (BASELINE.json configs[2], the config the metric's target is quoted on):
+  dense_fa forward, bf16, seq N=8192, head dim d=128, batch*heads B=16*32=512 per GPU.
+A "step" is one dense_fa forward over that batch.  One rank per GPU; the path shards over the
+trailing batch dim with no collective, so N GPUs = N independent shards ("weak").
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            # our CUDA path
+  python bench.py --impl reference --steps 2 --warmup 1     # CPU restatement of the reference
+  torchrun ... bench.py --gpus N ...                        # one rank per GPU
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launch stream, barrier +
+synchronize on both sides, max over ranks; inputs (3 GiB) exceed L2 (126 MB).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "flashattention.jl_b200"))
+
+N, D, B_PER_GPU = 8192, 128, 512
+WORKLOAD = "dense_fa fwd bf16 N=8192 d=128 B=512(16x32 heads) per GPU [BASELINE configs[2]]"
+FLOPS_PER_BATCH_ELT = 4.0 * N * N * D            # 4 N^2 d (softmax flops excluded), BASELINE.md section 3
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"bf16_tflops": j.get("bf16_tflops"), "bf16_tflops_sustained": j.get("bf16_tflops_sustained"),
+                "hbm_gbs": j.get("hbm_gbs"), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.stop_flag, self.th = gpu_index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_tflops(steps, warmup, batch_sample):
+    """CPU restatement of the reference (oracle port; the Julia reference cannot run here) on a
+    bounded sample of the workload: Float32, same N and d, `batch_sample` batch elements, all host
+    cores as the reference's `@threads` would use (src/dense.jl:45)."""
+    import numpy as np
+    from oracle import fa_oracle as fo
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    q, k, v = (np.asfortranarray(rng.standard_normal((N, D, batch_sample), dtype=np.float32)) for _ in range(3))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fo.dense_fa(q, k, v, threads=cores)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return FLOPS_PER_BATCH_ELT * batch_sample / t / 1e12, t, cores
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU path (restated) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 4
+    val, t, cores = cpu_reference_tflops(args.steps, args.warmup, sample_b)
+    line = {
+        "impl": "reference", "metric": "dense_fa forward attention TFLOP/s (4*N^2*d*B / time)", "value": val,
+        "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic randn (seeded)",
+        "config": {"workload": WORKLOAD, "sample": f"B={sample_b} of {B_PER_GPU} batch elements per step, Float32"},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle dense_fa (numpy restatement of src/dense.jl:21-102), N={N} d={D} B={sample_b}, "
+                                   f"{cores} threads over (batch,row-block) tasks"},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "tokens_per_s": sample_b * N / t,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="batch*heads per GPU (default: the named config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import fa_sm100a as fa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Bn = args.batch
+    warmup = max(args.warmup, 3)
+
+    # synthetic inputs of the named shape, generated on the host in Float32 and cast
+    bf = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+
+    def make(seed_shift):
+        t = fa.jl_empty((N, D, Bn), bf, dev)
+        base = t.permute(2, 1, 0)                     # C-contiguous (B, d, N)
+        for b0 in range(0, Bn, 64):                   # chunked: bounded host memory
+            nb = min(64, Bn - b0)
+            base[b0:b0 + nb].copy_(torch.randn(nb, D, N, generator=g, dtype=torch.float32).to(bf))
+        return t
+
+    q, k, v = make(0), make(1), make(2)
+    O = fa.jl_empty((N, D, Bn), bf, dev)
+    l = fa.jl_empty((N, 1, Bn), torch.float32, dev)
+    m = fa.jl_empty((N, 1, Bn), torch.float32, dev)
+
+    def step():
+        fa.dense_fa_(O, l, m, q, k, v)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    assert fa.last_path() == "tc", "headline config must run on the tcgen05 path"
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    total_flops = FLOPS_PER_BATCH_ELT * Bn * world
+    value = total_flops / (ms * 1e-3) / 1e12
+    per_gpu = value / world
+
+    # ---- end to end: host (pinned) buffers through the public API, H2D + kernel + D2H every step
+    e2e = None
+    if not args.no_e2e:
+        Be = min(Bn, 128)                              # bounded pinned host memory (1 GiB of tensors)
+        hq, hk, hv = (fa.jl_empty((N, D, Be), bf, "cpu") for _ in range(3))
+        for t_h, t_d in ((hq, q), (hk, k), (hv, v)):
+            t_h.permute(2, 1, 0).copy_(t_d.permute(2, 1, 0)[:Be])
+        hq, hk, hv = (fa.jl_array(t.permute(2, 1, 0).contiguous().pin_memory().permute(2, 1, 0)) for t in (hq, hk, hv))
+        hO = fa.jl_array(torch.empty(Be, D, N, dtype=bf).pin_memory().permute(2, 1, 0))
+        hl = fa.jl_array(torch.empty(Be, 1, N, dtype=torch.float32).pin_memory().permute(2, 1, 0))
+        hm = fa.jl_array(torch.empty(Be, 1, N, dtype=torch.float32).pin_memory().permute(2, 1, 0))
+        fa.dense_fa_(hO, hl, hm, hq, hk, hv)           # warm-up (allocations, first touch)
+        barrier()
+        t0 = time.perf_counter()
+        ne = 3
+        for _ in range(ne):
+            fa.dense_fa_(hO, hl, hm, hq, hk, hv)       # synchronises before returning
+        barrier()
+        te = (time.perf_counter() - t0) / ne
+        if world > 1:
+            tm = torch.tensor([te], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            te = float(tm.item())
+        e2e = {"value": FLOPS_PER_BATCH_ELT * Be * world / te / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": 3 * N * D * Be * 2, "d2h_bytes_per_step": N * D * Be * 2 + 2 * N * Be * 4,
+               "batch_per_gpu": Be, "ms_per_step": te * 1e3,
+               "api": "fa_dense_fwd_host via fa_sm100a.dense_fa_ on pinned CPU tensors"}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        roof = {"bound": "tensor", "achieved": per_gpu, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": per_gpu / peaks["bf16_tflops"], "traffic": None,
+                "peak_source": peaks["source"] + " burst (cuBLAS bf16 GEMM)",
+                "frac_of_sustained": per_gpu / peaks["bf16_tflops_sustained"],
+                "frac_of_nominal_2250": per_gpu / 2250.0,
+                "kernel": "tc_fwd_kernel<128,bf16>", "algorithmic_flops_per_launch": FLOPS_PER_BATCH_ELT * Bn,
+                "kernel_ms": ms}
+        line = {
+            "metric": "dense_fa forward attention TFLOP/s (4*N^2*d*B / time)", "value": value, "unit": "TFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic randn (seeded, generated Float32 on host then cast)",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": Bn, "l2": "inputs (3 GiB) larger than L2; no flush needed",
+                       "sharding": "batch*heads across ranks, no collective"},
+            "tokens_per_s": Bn * N * world / (ms * 1e-3), "tokens_per_s_batch_only": 16 * N * world * (Bn / 512) / (ms * 1e-3),
+            "gpu_launches": args.steps, "clocks": clocks, "roofline": roof, "e2e": e2e,
+        }
+        if not args.no_cpu:
+            cv, ct, cores = cpu_reference_tflops(1, 1, 2)
+            line["cpu_baseline"] = {"value": cv, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle dense_fa Float32 N={N} d={D} B=2 ({ct:.2f} s/step), {cores} threads; "
+                                              "CPU restatement of reference (Julia runtime unavailable)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

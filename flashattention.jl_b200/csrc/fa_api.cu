@@ -1,0 +1,464 @@
+// fa_api.cu -- the extern "C" surface of libfa_sm100a.so (see include/fa_sm100a.h).
+// Argument validation mirrors the reference's Julia signatures (same shapes, same defaults,
+// errors instead of MethodError/assertion); dispatch picks the tcgen05 path for 16-bit dense /
+// circulant forward and the exact-fp32 SIMT path otherwise.  There is no CPU fallback.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "fa_common.cuh"
+
+namespace fa {
+
+static thread_local char g_err[512] = "";
+static thread_local char g_path[64] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void set_path(const char* name) { snprintf(g_path, sizeof(g_path), "%s", name); }
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return FA_ERR_CUDA;
+}
+
+int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
+             int lbo, int sbo, int kstep, int kbox, cudaStream_t st);
+
+namespace {
+
+bool valid_dtype(int dt) { return dt == FA_F32 || dt == FA_F16 || dt == FA_BF16; }
+
+int check_common(int64_t N, int64_t d, int64_t dv, int64_t B, int dtype) {
+  if (!valid_dtype(dtype)) { set_error("dtype must be FA_F32, FA_F16 or FA_BF16 (got %d)", dtype); return FA_ERR_INVALID; }
+  if (N <= 0 || d <= 0 || dv <= 0 || B <= 0) { set_error("N, d, dv, B must be positive (got %lld, %lld, %lld, %lld)", (long long)N, (long long)d, (long long)dv, (long long)B); return FA_ERR_INVALID; }
+  if (N > 0x7fffffffLL || d > 4096 || dv > 4096) { set_error("dimension out of range"); return FA_ERR_INVALID; }
+  return FA_OK;
+}
+
+int need_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (libfa_sm100a has no CPU fallback)");
+    return FA_ERR_CUDA;
+  }
+  return FA_OK;
+}
+
+Geo dense_geo(int64_t N, int64_t d, int64_t dv, int64_t B) {
+  Geo g;
+  memset(&g, 0, sizeof(g));
+  g.mode = MODE_DENSE; g.d = (int)d; g.dv = (int)dv; g.N = N; g.B = B;
+  g.tau = 1.0f / sqrtf((float)d);                     // reference src/dense.jl:43
+  return g;
+}
+
+int windowed_geo(Geo& g, int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B, int64_t W,
+                 int64_t stride, int64_t pad) {
+  if (ndim < 1 || ndim > 3 || !dims) { set_error("ndim must be 1, 2 or 3"); return FA_ERR_INVALID; }
+  if (W <= 0 || stride <= 0 || pad < 0) { set_error("need W > 0, stride > 0, pad >= 0"); return FA_ERR_INVALID; }
+  memset(&g, 0, sizeof(g));
+  g.mode = MODE_WINDOWED; g.d = (int)d; g.dv = (int)dv; g.B = B; g.nd = ndim;
+  g.W = (int)W; g.stride = (int)stride; g.pad = (int)pad;
+  g.tau = 1.0f / sqrtf((float)d);
+  long long N = 1, L = 1, WD = 1;
+  for (int k = 0; k < 3; ++k) { g.s[k] = 1; g.o[k] = 1; }
+  for (int k = 0; k < ndim; ++k) {
+    if (dims[k] <= 0 || dims[k] > 0x7fffffffLL) { set_error("bad spatial extent"); return FA_ERR_INVALID; }
+    const long long o = (dims[k] + 2 * pad - W) / stride + 1;      // NNlib output size
+    if (dims[k] + 2 * pad < W || o <= 0) { set_error("window (%lld) larger than padded extent (%lld + 2*%lld)", (long long)W, (long long)dims[k], (long long)pad); return FA_ERR_INVALID; }
+    g.s[k] = (int)dims[k]; g.o[k] = (int)o;
+    N *= dims[k]; L *= o; WD *= W;
+    if (WD > 0x7fffffffLL || N > 0x7fffffffLL) { set_error("window or volume too large"); return FA_ERR_INVALID; }
+  }
+  g.N = N; g.L = L; g.WD = (int)WD;
+  g.overlap = stride < W ? 1 : 0;
+  return FA_OK;
+}
+
+// does every spatial position belong to at least one window?
+bool full_cover(const Geo& g) {
+  for (int k = 0; k < g.nd; ++k)
+    for (int pos = 0; pos < g.s[k]; ++pos) {
+      Geo g1 = g; g1.nd = 1; g1.s[0] = g.s[k]; g1.o[0] = g.o[k];
+      if (window_count_at(g1, pos) == 0) return false;
+    }
+  return true;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+int fa_version(void) { return FA_VERSION_MAJOR * 100 + FA_VERSION_MINOR; }
+const char* fa_last_error_string(void) { return g_err; }
+const char* fa_last_path(void) { return g_path; }
+int fa_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ------------------------------------------------------------------------------ index sets
+int fa_circulant_index(int64_t N, int64_t W, int64_t* keys) {
+  if (N <= 0 || W <= 0 || W > N || !keys) { set_error("need 0 < W <= N and a keys buffer"); return FA_ERR_INVALID; }
+  const int64_t p = (W - 1) / 2;                                       // src/utils.jl:8
+  for (int64_t j = 1; j <= N; ++j)
+    for (int64_t w = 1; w <= W; ++w) {
+      int64_t m = w;                                                   // :10
+      if (j <= p) m = ((m - 1 - (j - p - 1)) % W + W) % W + 1;         // :11-12
+      else if (j > N - p) m = ((m - 1 - (p - N + j)) % W + W) % W + 1; // :13
+      const int64_t i = (((m - 1) + (j - 1) - p) % N + N) % N + 1;     // :15
+      keys[(j - 1) * W + (w - 1)] = i - 1;
+    }
+  return FA_OK;
+}
+
+int fa_window_index(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                    int64_t* n_windows, int64_t* idx) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, 1, 1, 1, W, stride, pad);
+  if (rc) return rc;
+  if (n_windows) for (int k = 0; k < ndim; ++k) n_windows[k] = g.o[k];
+  if (idx)
+    for (long long w = 0; w < g.L; ++w)
+      for (int s = 0; s < g.WD; ++s) idx[w * g.WD + s] = window_slot_token(g, w, s);
+  return FA_OK;
+}
+
+int fa_window_count(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad, int64_t* cnt) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, 1, 1, 1, W, stride, pad);
+  if (rc) return rc;
+  if (!cnt) { set_error("cnt is NULL"); return FA_ERR_INVALID; }
+  for (long long t = 0; t < g.N; ++t) cnt[t] = window_count_at(g, t);
+  return FA_OK;
+}
+
+// ------------------------------------------------------------------------------ dense
+int fa_dense_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                 int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags, void* stream) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if ((rc = need_device())) return rc;
+  const Geo g = dense_geo(N, d, dv, B);
+  FwdArgs a{q, k, v, o, nullptr, l, m};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(g, dtype)) { set_path("tc"); return tc_fwd(g, a, dtype, st); }
+  set_path("simt");
+  return simt_fwd(g, a, dtype, st);
+}
+
+size_t fa_workspace_bytes_dense_bwd(int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags) {
+  (void)d; (void)dv; (void)dtype; (void)flags;
+  return align256((size_t)N * B * sizeof(float));          // delta
+}
+
+int fa_dense_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                 const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                 int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !d_o || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (!workspace || workspace_bytes < fa_workspace_bytes_dense_bwd(N, d, dv, B, dtype, flags)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
+  if ((rc = need_device())) return rc;
+  const Geo g = dense_geo(N, d, dv, B);
+  BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
+  set_path("simt");
+  return simt_bwd(g, a, dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ circulant
+static int circ_geo(Geo& g, int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W) {
+  if (W <= 0 || W > N) { set_error("circulant window must satisfy 0 < W <= N (got W=%lld, N=%lld)", (long long)W, (long long)N); return FA_ERR_INVALID; }
+  g = dense_geo(N, d, dv, B);
+  g.mode = MODE_CIRCULANT; g.W = (int)W; g.p = (int)((W - 1) / 2);     // src/utils.jl:8
+  return FA_OK;
+}
+
+int fa_circulant_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                     int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags, void* stream) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  Geo g;
+  if ((rc = circ_geo(g, N, d, dv, B, W))) return rc;
+  if ((rc = need_device())) return rc;
+  FwdArgs a{q, k, v, o, nullptr, l, m};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(g, dtype)) { set_path("tc"); return tc_fwd(g, a, dtype, st); }
+  set_path("simt");
+  return simt_fwd(g, a, dtype, st);
+}
+
+size_t fa_workspace_bytes_circulant_bwd(int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags) {
+  (void)W;
+  return fa_workspace_bytes_dense_bwd(N, d, dv, B, dtype, flags);
+}
+
+int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                     const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                     int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !d_o || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  Geo g;
+  if ((rc = circ_geo(g, N, d, dv, B, W))) return rc;
+  if (!workspace || workspace_bytes < fa_workspace_bytes_circulant_bwd(N, d, dv, B, W, dtype, flags)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
+  if ((rc = need_device())) return rc;
+  BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
+  set_path("simt");
+  return simt_bwd(g, a, dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ windowed
+size_t fa_workspace_bytes_windowed_fwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                                       int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
+  (void)dtype; (void)flags;
+  Geo g;
+  if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
+  return g.overlap ? align256((size_t)g.N * dv * B * sizeof(float)) : 256;
+}
+
+int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                    int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                    int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
+  if (!q || !k || !v || !y || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (g.overlap && (!workspace || workspace_bytes < fa_workspace_bytes_windowed_fwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags))) {
+    set_error("workspace too small"); return FA_ERR_WORKSPACE;
+  }
+  if ((rc = need_device())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FwdArgs a{q, k, v, y, nullptr, l, m};
+  set_path("simt");
+  if (g.overlap) {
+    a.acc = static_cast<float*>(workspace);
+    FA_CUDA_TRY(cudaMemsetAsync(a.acc, 0, (size_t)g.N * dv * B * sizeof(float), st));
+    if ((rc = simt_fwd(g, a, dtype, st))) return rc;
+    return fold_finalize(g, a.acc, y, (int)dv, dtype, /*divide=*/1, st);     // src/windowed.jl:19
+  }
+  if ((rc = simt_fwd(g, a, dtype, st))) return rc;
+  if (!full_cover(g)) return fill_uncovered_nan(g, y, (int)dv, dtype, st);   // 0/0 = NaN
+  return FA_OK;
+}
+
+size_t fa_workspace_bytes_windowed_bwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                                       int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
+  (void)dtype; (void)flags;
+  Geo g;
+  if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
+  size_t bytes = align256((size_t)g.WD * g.L * B * sizeof(float));                 // delta per window slot
+  if (g.overlap) bytes += 2 * align256((size_t)g.N * d * B * sizeof(float)) + align256((size_t)g.N * dv * B * sizeof(float));
+  return bytes;
+}
+
+int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y,
+                    const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                    int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                    int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
+  if (!q || !k || !v || !d_y || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (!workspace || workspace_bytes < fa_workspace_bytes_windowed_bwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags)) {
+    set_error("workspace too small"); return FA_ERR_WORKSPACE;
+  }
+  if ((rc = need_device())) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  BwdArgs a{q, k, v, nullptr, d_y, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, reinterpret_cast<float*>(ws)};
+  ws += align256((size_t)g.WD * g.L * B * sizeof(float));
+  const size_t esz = dtype_size(dtype);
+  set_path("simt");
+  if (g.overlap) {
+    const size_t nq = (size_t)g.N * d * B, nv = (size_t)g.N * dv * B;
+    a.aq = reinterpret_cast<float*>(ws); ws += align256(nq * 4);
+    a.ak = reinterpret_cast<float*>(ws); ws += align256(nq * 4);
+    a.av = reinterpret_cast<float*>(ws);
+    FA_CUDA_TRY(cudaMemsetAsync(a.aq, 0, nq * 4, st));
+    FA_CUDA_TRY(cudaMemsetAsync(a.ak, 0, nq * 4, st));
+    FA_CUDA_TRY(cudaMemsetAsync(a.av, 0, nv * 4, st));
+    if ((rc = simt_bwd(g, a, dtype, st))) return rc;
+    if ((rc = fold_finalize(g, a.aq, dq, (int)d, dtype, 0, st))) return rc;   // adjoint of unfold: fold, no division
+    if ((rc = fold_finalize(g, a.ak, dk, (int)d, dtype, 0, st))) return rc;
+    return fold_finalize(g, a.av, dv_out, (int)dv, dtype, 0, st);
+  }
+  if (!full_cover(g)) {   // uncovered positions receive no gradient
+    FA_CUDA_TRY(cudaMemsetAsync(dq, 0, (size_t)g.N * d * B * esz, st));
+    FA_CUDA_TRY(cudaMemsetAsync(dk, 0, (size_t)g.N * d * B * esz, st));
+    FA_CUDA_TRY(cudaMemsetAsync(dv_out, 0, (size_t)g.N * dv * B * esz, st));
+  }
+  return simt_bwd(g, a, dtype, st);
+}
+
+// ------------------------------------------------------------------------------ unfold / fold
+int fa_window(const void* x, void* xw, int ndim, const int64_t* dims, int64_t d, int64_t B,
+              int64_t W, int64_t stride, int64_t pad, int dtype, void* stream) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, d, B, W, stride, pad);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, d, B, dtype))) return rc;
+  if (!x || !xw) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if ((rc = need_device())) return rc;
+  return window_gather(g, x, xw, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int fa_unwindow(const void* xw, void* x, int ndim, const int64_t* dims, int64_t d, int64_t B,
+                int64_t W, int64_t stride, int64_t pad, int dtype, void* stream) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, d, B, W, stride, pad);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, d, B, dtype))) return rc;
+  if (!x || !xw) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if ((rc = need_device())) return rc;
+  return window_scatter(g, xw, x, dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ softmax
+int fa_softmax(void* out, const void* in, int64_t M, int64_t N, int64_t B, int dim, int dtype, void* stream) {
+  if (dim != 1 && dim != 2) { set_error("only softmax in dims 1 or 2 supported"); return FA_ERR_INVALID; }   // src/fused_softmax.jl:12
+  if (!valid_dtype(dtype) || M <= 0 || N <= 0 || B <= 0 || !out || !in) { set_error("bad softmax arguments"); return FA_ERR_INVALID; }
+  int rc = need_device();
+  if (rc) return rc;
+  return softmax_launch(out, in, M, N, B, dim, dtype, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------ host buffers
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) { FA_CUDA_TRY(cudaMalloc(&p, n ? n : 1)); return FA_OK; }
+};
+
+// Batch-chunked pipeline: H2D of chunk i+1 overlaps the kernels of chunk i and the D2H of
+// chunk i-1 (three streams).  `run(b0, nb, dq, dk, dv, do, dl, dm, stream)` enqueues the kernels.
+template <typename Run>
+int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                  size_t q_elems_per_b, size_t v_elems_per_b, size_t stat_per_b, int64_t B, int dtype,
+                  int device, Run run) {
+  int rc = need_device();
+  if (rc) return rc;
+  FA_CUDA_TRY(cudaSetDevice(device));
+  const size_t esz = dtype_size(dtype);
+  const size_t per_b = (2 * q_elems_per_b + 2 * v_elems_per_b) * esz + 2 * stat_per_b * 4;
+  int64_t chunk = B;
+  const size_t target = (size_t)256 << 20;                 // ~256 MiB of tensors in flight per chunk
+  if (per_b * (size_t)B > 2 * target) { chunk = (int64_t)(target / per_b); if (chunk < 1) chunk = 1; }
+  const int nbuf = chunk < B ? 2 : 1;
+  DevBuf dq[2], dk[2], dvv[2], dout[2], dl[2], dm[2];
+  for (int i = 0; i < nbuf; ++i) {
+    if ((rc = dq[i].alloc(chunk * q_elems_per_b * esz))) return rc;
+    if ((rc = dk[i].alloc(chunk * q_elems_per_b * esz))) return rc;
+    if ((rc = dvv[i].alloc(chunk * v_elems_per_b * esz))) return rc;
+    if ((rc = dout[i].alloc(chunk * v_elems_per_b * esz))) return rc;
+    if ((rc = dl[i].alloc(chunk * stat_per_b * 4))) return rc;
+    if ((rc = dm[i].alloc(chunk * stat_per_b * 4))) return rc;
+  }
+  cudaStream_t s[2];
+  cudaEvent_t done[2];
+  for (int i = 0; i < 2; ++i) { FA_CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)); FA_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); }
+  int it = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
+    const int i = it % nbuf;
+    const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    cudaStream_t st = s[it % 2];
+    if (it >= nbuf) FA_CUDA_TRY(cudaStreamWaitEvent(st, done[i], 0));       // buffer i free again
+    const char* hq = static_cast<const char*>(q) + b0 * q_elems_per_b * esz;
+    const char* hk = static_cast<const char*>(k) + b0 * q_elems_per_b * esz;
+    const char* hv = static_cast<const char*>(v) + b0 * v_elems_per_b * esz;
+    FA_CUDA_TRY(cudaMemcpyAsync(dq[i].p, hq, nb * q_elems_per_b * esz, cudaMemcpyHostToDevice, st));
+    FA_CUDA_TRY(cudaMemcpyAsync(dk[i].p, hk, nb * q_elems_per_b * esz, cudaMemcpyHostToDevice, st));
+    FA_CUDA_TRY(cudaMemcpyAsync(dvv[i].p, hv, nb * v_elems_per_b * esz, cudaMemcpyHostToDevice, st));
+    if ((rc = run(nb, dq[i].p, dk[i].p, dvv[i].p, dout[i].p, static_cast<float*>(dl[i].p), static_cast<float*>(dm[i].p), st))) return rc;
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(o) + b0 * v_elems_per_b * esz, dout[i].p, nb * v_elems_per_b * esz, cudaMemcpyDeviceToHost, st));
+    FA_CUDA_TRY(cudaMemcpyAsync(l + b0 * stat_per_b, dl[i].p, nb * stat_per_b * 4, cudaMemcpyDeviceToHost, st));
+    FA_CUDA_TRY(cudaMemcpyAsync(m + b0 * stat_per_b, dm[i].p, nb * stat_per_b * 4, cudaMemcpyDeviceToHost, st));
+    FA_CUDA_TRY(cudaEventRecord(done[i], st));
+  }
+  for (int i = 0; i < 2; ++i) FA_CUDA_TRY(cudaStreamSynchronize(s[i]));
+  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(s[i]); cudaEventDestroy(done[i]); }
+  return FA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fa_dense_fwd_host(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                      int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags, int device) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  return host_pipeline(q, k, v, o, l, m, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, device,
+      [&](int64_t nb, void* dq, void* dk, void* dvp, void* dop, float* dl, float* dm, cudaStream_t st) {
+        return fa_dense_fwd(dq, dk, dvp, dop, dl, dm, N, d, dv, nb, dtype, flags, st);
+      });
+}
+
+int fa_circulant_fwd_host(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                          int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags, int device) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  return host_pipeline(q, k, v, o, l, m, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, device,
+      [&](int64_t nb, void* dq, void* dk, void* dvp, void* dop, float* dl, float* dm, cudaStream_t st) {
+        return fa_circulant_fwd(dq, dk, dvp, dop, dl, dm, N, d, dv, nb, W, dtype, flags, st);
+      });
+}
+
+int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                         int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int dtype, int flags, int device) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
+  if (!q || !k || !v || !y || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if ((rc = need_device())) return rc;
+  FA_CUDA_TRY(cudaSetDevice(device));
+  // workspace sized for the largest chunk the pipeline can hand us (<= B)
+  const size_t wsb = fa_workspace_bytes_windowed_fwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags);
+  DevBuf ws[2];
+  if ((rc = ws[0].alloc(wsb))) return rc;
+  if ((rc = ws[1].alloc(wsb))) return rc;
+  int turn = 0;
+  return host_pipeline(q, k, v, y, l, m, (size_t)g.N * d, (size_t)g.N * dv, (size_t)g.WD * g.L, B, dtype, device,
+      [&](int64_t nb, void* dq, void* dk, void* dvp, void* dop, float* dl, float* dm, cudaStream_t st) {
+        void* w = ws[turn++ % 2].p;
+        return fa_windowed_fwd(dq, dk, dvp, dop, dl, dm, ndim, dims, d, dv, nb, W, stride, pad, dtype, flags, w, wsb, st);
+      });
+}
+
+// ------------------------------------------------------------------------------ diagnostics
+// One UMMA tile with caller-supplied descriptor fields (see fa_tc_probe.cu).  Not a product API.
+int fa_debug_umma_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
+                        int lbo, int sbo, int kstep, int kbox, void* stream) {
+  int rc = need_device();
+  if (rc) return rc;
+  return tc_probe(mode, a, b, p, out, D, dtype, lbo, sbo, kstep, kbox, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

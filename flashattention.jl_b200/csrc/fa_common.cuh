@@ -1,0 +1,142 @@
+// fa_common.cuh -- shared host/device definitions for libfa_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "../../include/fa_sm100a.h"
+
+namespace fa {
+
+// ---------------------------------------------------------------------------------------
+// Geometry of one attention call.  "Slots" are rows/columns of one independent attention
+// problem:  dense/circulant -> one problem per batch element, slot == token;
+//           windowed        -> one problem per (window, batch), slot == position inside the
+//                              window (kappa, first-dim-fastest), gathered on the fly from the
+//                              (spatial..., d, B) tensor with zero fill outside (the fused
+//                              `window`/`unwindow` of reference src/utils.jl:36-54).
+// ---------------------------------------------------------------------------------------
+enum Mode : int { MODE_DENSE = 0, MODE_CIRCULANT = 1, MODE_WINDOWED = 2 };
+
+struct Geo {
+  int mode;
+  int d, dv;
+  int nd;            // spatial dims (windowed)
+  int s[3];          // spatial extents (windowed), s[0] fastest
+  int o[3];          // windows per dim (windowed)
+  int W;             // window size (circulant: band width; windowed: per-dim window)
+  int stride, pad;   // windowed
+  int WD;            // W^nd slots per window (windowed)
+  int p;             // (W-1)/2 (circulant)
+  int overlap;       // windowed: 1 if a position can be covered by >1 window (fold needs +=)
+  long long N;       // tokens per batch element
+  long long L;       // windows per batch element (windowed)
+  long long B;       // batch elements
+  float tau;         // 1/sqrt(d)
+};
+
+__host__ __device__ inline long long geo_problems(const Geo& g) {
+  return g.mode == MODE_WINDOWED ? g.L * g.B : g.B;
+}
+__host__ __device__ inline long long geo_slots(const Geo& g) {
+  return g.mode == MODE_WINDOWED ? (long long)g.WD : g.N;
+}
+
+// token (0-based linear spatial index) read by slot `slot` of window `win`, or -1 for padding
+__host__ __device__ inline long long window_slot_token(const Geo& g, long long win, int slot) {
+  long long tok = 0, mult = 1;
+  for (int k = 0; k < g.nd; ++k) {
+    const int wk = (int)(win % g.o[k]);  win /= g.o[k];
+    const int kk = slot % g.W;           slot /= g.W;
+    const int pos = wk * g.stride - g.pad + kk;
+    if (pos < 0 || pos >= g.s[k]) return -1;
+    tok += pos * mult;
+    mult *= g.s[k];
+  }
+  return tok;
+}
+
+// number of windows covering spatial token `tok` (the divisor of src/windowed.jl:16-17)
+__host__ __device__ inline int window_count_at(const Geo& g, long long tok) {
+  int cnt = 1;
+  for (int k = 0; k < g.nd; ++k) {
+    const int pos = (int)(tok % g.s[k]);  tok /= g.s[k];
+    const int a = pos + g.pad;                         // 0 <= a - w*stride < W
+    int wmax = a / g.stride;
+    if (wmax > g.o[k] - 1) wmax = g.o[k] - 1;
+    int lo = a - g.W + 1;
+    int wmin = lo <= 0 ? 0 : (lo + g.stride - 1) / g.stride;
+    const int c = wmax - wmin + 1;
+    cnt *= (c > 0 ? c : 0);
+  }
+  return cnt;
+}
+
+__host__ __device__ inline long long pmod(long long a, long long n) {
+  long long r = a % n;
+  return r < 0 ? r + n : r;
+}
+
+// ---------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T x);
+template <> __device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+inline size_t dtype_size(int dtype) { return dtype == FA_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (thread-local message, status codes across the C ABI)
+// ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void set_path(const char* name);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define FA_CUDA_TRY(expr)                                   \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return fa::cuda_fail(_e, #expr); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// launchers implemented in the .cu files
+// ---------------------------------------------------------------------------------------
+struct FwdArgs {
+  const void *q, *k, *v;
+  void* o;          // dense/circulant: output; windowed non-overlap: y; windowed overlap: unused
+  float* acc;       // windowed overlap: fp32 fold accumulator (N*dv*B), zero-initialised
+  float *l, *m;
+};
+struct BwdArgs {
+  const void *q, *k, *v, *o, *d_o;
+  const float *l, *m;
+  void *dq, *dk, *dv;      // dense/circulant/windowed non-overlap: final outputs
+  float *aq, *ak, *av;     // windowed overlap: fp32 fold accumulators, zero-initialised
+  float* delta;            // D_i = rowsum(dO o O) per slot, (slots * problems) floats
+};
+
+int simt_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
+int simt_bwd(const Geo& g, const BwdArgs& a, int dtype, cudaStream_t st);
+int fold_finalize(const Geo& g, const float* acc, void* y, int channels, int dtype, int divide,
+                  cudaStream_t st);
+int fill_uncovered_nan(const Geo& g, void* y, int channels, int dtype, cudaStream_t st);
+int window_gather(const Geo& g, const void* x, void* xw, int dtype, cudaStream_t st);
+int window_scatter(const Geo& g, const void* xw, void* x, int dtype, cudaStream_t st);
+int softmax_launch(void* out, const void* in, long long M, long long N, long long B, int dim,
+                   int dtype, cudaStream_t st);
+
+// tensor-core (tcgen05) forward: dense + circulant, 16-bit dtypes, d == dv in {64,128}
+bool tc_fwd_supported(const Geo& g, int dtype);
+int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
+
+}  // namespace fa

@@ -1,0 +1,130 @@
+// fa_tc_probe.cu -- diagnostics: one 128x128 UMMA tile with caller-supplied descriptor fields.
+// Used by tests/test_gpu_probe.py to pin the shared-memory descriptor conventions (MN-major
+// SWIZZLE_128B for Q/K, K-major SWIZZLE_128B for V, P operand in TMEM) on real hardware,
+// independently of the full attention pipeline.  Not part of the product path.
+#include <cuda.h>
+#include "fa_common.cuh"
+#include "fa_ptx.cuh"
+
+namespace fa {
+int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B);
+
+namespace {
+using namespace ptx;
+
+struct ProbeParams {
+  int mode;         // 0: S = A^T B (both MN-major from smem);  1: O = P V (P in TMEM, V K-major smem)
+  int D;            // channels (64 or 128)
+  int fmt;          // 0 f16, 1 bf16
+  int lbo, sbo;     // descriptor byte offsets for the smem operands
+  int kstep;        // byte advance of the start address per K=16 step (within a 64-wide box)
+  int kbox;         // k-steps per box before jumping by box_bytes (mode 1); 0 = never
+  const float* p;   // mode 1: P [128][128] fp32 row-major
+  float* out;       // mode 0: [128][128]; mode 1: [128][D]   (row-major fp32)
+};
+
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const ProbeParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int D = prm.D;
+  const uint32_t box = 64u * D * 2u, tile = 2u * box;
+  const uint32_t sA = sbase, sB = sbase + tile, bars = sbase + 2 * tile, slot = bars + 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bars, 1); mbar_init(bars + 8, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+
+  if (prm.mode == 1) {
+    // P row of this thread -> 16-bit pairs -> TMEM columns [0,64)
+    const float* pr = prm.p + (size_t)(warp * 32 + lane) * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = pr[32 * c + 2 * i], b = pr[32 * c + 2 * i + 1];
+        if (prm.fmt == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
+        else { __half2 h = __floats2half2_rn(a, b); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
+      }
+      tmem_st16(tmem_base + lane_addr + 16 * c, pk);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = prm.mode == 0 ? 2 * tile : tile;
+    mbar_arrive_expect_tx(bars, bytes);
+    if (prm.mode == 0) {
+      tma_load_3d(sA, &tma_a, bars, 0, 0, 0);
+      tma_load_3d(sA + box, &tma_a, bars, 64, 0, 0);
+    }
+    tma_load_3d(sB, &tma_b, bars, 0, 0, 0);
+    tma_load_3d(sB + box, &tma_b, bars, 64, 0, 0);
+    mbar_wait(bars, 0);
+    tc_fence_after();
+    if (prm.mode == 0) {
+      const uint32_t idesc = make_idesc_f16(prm.fmt, 1, 1, 128, 128);
+      for (int ks = 0; ks < D / 16; ++ks) {
+        const uint64_t ad = make_smem_desc_sw128(sA + ks * prm.kstep, prm.lbo, prm.sbo);
+        const uint64_t bd = make_smem_desc_sw128(sB + ks * prm.kstep, prm.lbo, prm.sbo);
+        mma_ss(tmem_base + 128, ad, bd, idesc, ks > 0);
+      }
+    } else {
+      const uint32_t idesc = make_idesc_f16(prm.fmt, 0, 0, 128, D);
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t off = prm.kbox ? (ks / prm.kbox) * box + (ks % prm.kbox) * prm.kstep : ks * prm.kstep;
+        const uint64_t bd = make_smem_desc_sw128(sB + off, prm.lbo, prm.sbo);
+        mma_ts(tmem_base + 128, tmem_base + ks * 8, bd, idesc, ks > 0);
+      }
+    }
+    tc_commit(bars + 8);
+  }
+  __syncwarp();
+  mbar_wait(bars + 8, 0);
+  tc_fence_after();
+  const int ncol = prm.mode == 0 ? 128 : D;
+  float* orow = prm.out + (size_t)(warp * 32 + lane) * ncol;
+#pragma unroll 1
+  for (int c = 0; c < ncol / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + lane_addr + 128 + 32 * c, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) orow[32 * c + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+}  // namespace
+
+int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
+             int lbo, int sbo, int kstep, int kbox, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_public(&ta, a ? a : b, dtype, 128, D, 1))) return rc;
+  if ((rc = make_tmap_public(&tb, b, dtype, 128, D, 1))) return rc;
+  ProbeParams prm;
+  prm.mode = mode; prm.D = D; prm.fmt = dtype == FA_BF16 ? 1 : 0;
+  prm.lbo = lbo; prm.sbo = sbo; prm.kstep = kstep; prm.kbox = kbox; prm.p = p; prm.out = out;
+  const int smem = 4 * 64 * D * 2 + 64 + 1024;
+  FA_CUDA_TRY(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_kernel<<<1, 128, smem, st>>>(ta, tb, prm);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+}  // namespace fa

@@ -1,0 +1,140 @@
+/*
+ * fa_sm100a.h -- C ABI of libfa_sm100a.so, the B200 (sm_100a) backend behind the
+ * FlashAttention.jl API.
+ *
+ * The reference has no FFI: its boundary is the exported Julia API
+ * (reference src/FlashAttention.jl:13,20-21,26-27).  Each entry point below replaces the
+ * host-algorithm body of one exported function; the Julia wrapper keeps the reshape/allocate
+ * prologue (src/dense.jl:1-19 etc.) and does one `ccall`.
+ *
+ * Conventions
+ *  - Layout: Julia column-major `(spatial..., d, B)`, i.e. C `[B][d][N]` with the token index
+ *    contiguous (src/dense.jl:6-8).  All tensors dense/contiguous, 16-byte aligned.
+ *  - Device entry points take raw DEVICE pointers and a `cudaStream_t` (as `void*`; NULL = the
+ *    legacy default stream); they enqueue work and return without synchronising.
+ *  - `*_host` entry points take HOST pointers (the reference's `Array` arguments); they copy
+ *    in, run the same kernels, copy out and synchronise before returning.
+ *  - Ownership: the caller owns every buffer (inputs, outputs, workspace).  Nothing is retained.
+ *  - Softmax statistics `l`, `m` are always float32 (reference allocates them with eltype(Q),
+ *    src/dense.jl:12-13; for 16-bit inputs float32 is kept so backward can reuse them).
+ *  - Every function returns an `fa_status`; 0 = ok.  `fa_last_error_string()` returns a
+ *    thread-local message.  No exceptions or aborts cross the boundary.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point returns
+ *    FA_ERR_CUDA.
+ */
+#ifndef FA_SM100A_H_
+#define FA_SM100A_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_VERSION_MAJOR 0
+#define FA_VERSION_MINOR 1
+
+typedef enum fa_status {
+  FA_OK = 0,
+  FA_ERR_INVALID = 1,      /* bad argument (shape, dtype, NULL pointer, W > N, ...) */
+  FA_ERR_UNSUPPORTED = 2,  /* valid request that no kernel covers                */
+  FA_ERR_CUDA = 3,         /* CUDA runtime/driver error, or no device            */
+  FA_ERR_WORKSPACE = 4     /* workspace missing or too small                     */
+} fa_status;
+
+typedef enum fa_dtype {
+  FA_F32 = 0,   /* Float32: exact FFMA path (no TF32), parity 1e-5 */
+  FA_F16 = 1,   /* Float16: tcgen05 kind::f16, fp32 accumulate     */
+  FA_BF16 = 2   /* BFloat16: tcgen05 kind::f16, fp32 accumulate    */
+} fa_dtype;
+
+/* flags (bit set) */
+#define FA_FLAG_NONE 0
+#define FA_FLAG_FORCE_SIMT 1   /* never take the tensor-core path (debug / exact arithmetic) */
+
+/* ---- host helpers -------------------------------------------------------------------- */
+int fa_version(void);                       /* FA_VERSION_MAJOR*100 + FA_VERSION_MINOR     */
+const char* fa_last_error_string(void);     /* thread-local, never NULL                    */
+const char* fa_last_path(void);             /* thread-local name of the kernel family the last
+                                               compute call dispatched to ("simt", "tc")   */
+int fa_device_count(void);                  /* 0 when no CUDA device is usable             */
+
+/* ---- index sets (host, integer, bit-exact) --------------------------------------------- */
+/* reference src/utils.jl:6-17 cartesian_circulant: fills keys[W*N] (column-major (W,N)) with
+ * the 0-based key index of nz-entry w of query j, in the reference's storage order. */
+int fa_circulant_index(int64_t N, int64_t W, int64_t* keys);
+/* reference src/utils.jl:36-44 window (NNlib.unfold): fills idx[WD*L] (column-major (W^D,L))
+ * with the 0-based linear spatial index read by slot kappa of window w, -1 for zero padding;
+ * n_windows[ndim] receives the windows per dim.  Pass idx = NULL to query n_windows only. */
+int fa_window_index(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                    int64_t* n_windows, int64_t* idx);
+/* per-position window count (the `divisor` of src/windowed.jl:16-17): cnt[prod(dims)] */
+int fa_window_count(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                    int64_t* cnt);
+
+/* ---- dense: replaces dense_fa! (src/dense.jl:21-102) -------------------------------- */
+int fa_dense_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                 int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags, void* stream);
+/* replaces dense_fa_backward (src/dense.jl:104-167, broken) == OneDFastBack
+ * (src_cpp/FlashAttention.cpp:194-252) */
+size_t fa_workspace_bytes_dense_bwd(int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags);
+int fa_dense_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                 const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                 int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- circulant: replaces circulant_fa! (src/circulant.jl:9-118), 1-D, W <= N ----------- */
+int fa_circulant_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                     int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W,
+                     int dtype, int flags, void* stream);
+size_t fa_workspace_bytes_circulant_bwd(int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W,
+                                        int dtype, int flags);
+int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                     const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                     int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- windowed: replaces windowed_fa / block_fa (src/windowed.jl:1-23) with window/unwindow
+ *      (src/utils.jl:36-54) fused in.  q,k,v,y :: (dims[0..ndim), d|dv, B); l,m :: (W^D,1,L,B). */
+size_t fa_workspace_bytes_windowed_fwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                                       int64_t W, int64_t stride, int64_t pad, int dtype, int flags);
+int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                    int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                    int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t fa_workspace_bytes_windowed_bwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                                       int64_t W, int64_t stride, int64_t pad, int dtype, int flags);
+/* backward per SURVEY A.5.2 (no reference code): dYw = window(dY ./ count), per-window dense
+ * backward with P recomputed from (l, m), dq = unwindow(dQw) etc. */
+int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y,
+                    const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                    int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                    int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- standalone unfold/fold: window / unwindow (src/utils.jl:36-54) --------------------- */
+int fa_window(const void* x, void* xw, int ndim, const int64_t* dims, int64_t d, int64_t B,
+              int64_t W, int64_t stride, int64_t pad, int dtype, void* stream);
+int fa_unwindow(const void* xw, void* x, int ndim, const int64_t* dims, int64_t d, int64_t B,
+                int64_t W, int64_t stride, int64_t pad, int dtype, void* stream);
+
+/* ---- softmax: replaces fused_softmax! (src/fused_softmax.jl:11-39); in :: (M,N,B) column-major,
+ *      dim = 1 (columns) or 2 (rows); any other dim -> FA_ERR_INVALID (assertion at :12) */
+int fa_softmax(void* out, const void* in, int64_t M, int64_t N, int64_t B, int dim, int dtype,
+               void* stream);
+
+/* ---- host-buffer entry points (the reference's Array arguments; H2D + kernels + D2H) ---- */
+int fa_dense_fwd_host(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                      int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags, int device);
+int fa_circulant_fwd_host(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                          int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W,
+                          int dtype, int flags, int device);
+int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                         int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int dtype, int flags, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_SM100A_H_ */

@@ -1,0 +1,275 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libfa_sm100a.so) against the CPU oracle
+on the same seeded inputs.  Mirrors test/test.jl:5-21 and the `@test fa ~ dpa` checks of
+bench/compare.jl:20,47,74, plus backward and the edge cases of SURVEY A.3
+(zero-pad tokens, uncovered positions = NaN, overlapping windows, even/odd/full band).
+
+Tolerances (BASELINE.json north_star): 1e-5 for the exact-fp32 path, 2e-3 for bf16/fp16
+compute with fp32 accumulation; both as max-abs error relative to max-abs of the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fa_oracle as fo
+from util import randn_np, rel_err, sampled_dense_rows, to_dev, to_np, tol_for
+
+pytestmark = pytest.mark.gpu
+
+fa = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _load():
+    global fa
+    import fa_sm100a
+    fa = fa_sm100a
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert fa.lib.fa_device_count() >= 1
+
+
+F32, BF16, F16 = torch.float32, torch.bfloat16, torch.float16
+
+
+def _qkv(shape, dv, dtype, seeds=(0, 1, 2)):
+    vshape = shape[:-2] + (dv, shape[-1])
+    return [randn_np(s, sd, dtype) for s, sd in zip((shape, shape, vshape), seeds)]
+
+
+# ------------------------------------------------------------------------------- dense forward
+@pytest.mark.parametrize("shape,dv", [((30, 12, 2), 6), ((30, 12, 2), 12), ((1024, 64, 4), 64),
+                                      ((600, 64, 1), 64), ((7, 5, 3, 8, 2), 8), ((129, 128, 3), 128),
+                                      ((64, 100, 2), 36)])
+def test_dense_fwd_fp32(shape, dv):
+    q, k, v = _qkv(shape, dv, F32)
+    y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
+    y, l, m = fa.dense_fa(*(to_dev(t) for t in (q, k, v)))
+    assert fa.last_path() == "simt"
+    assert tuple(y.shape) == y0.shape and tuple(l.shape) == l0.shape
+    assert rel_err(to_np(y), y0) < 1e-5
+    assert rel_err(to_np(l), l0) < 1e-5
+    assert rel_err(to_np(m), m0) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("N,d,B", [(128, 64, 1), (256, 128, 2), (384, 64, 3), (1024, 64, 4), (2048, 128, 2),
+                                   (200, 64, 1), (1000, 128, 2), (72, 64, 2), (520, 128, 1)])
+def test_dense_fwd_tc(N, d, B, dtype):
+    q, k, v = _qkv((N, d, B), d, dtype)
+    y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
+    y, l, m = fa.dense_fa(*(to_dev(t, dtype) for t in (q, k, v)))
+    assert fa.last_path() == "tc"
+    assert y.dtype == dtype and l.dtype == torch.float32
+    assert rel_err(to_np(y), y0) < 2e-3
+    assert rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+def test_dense_fwd_16bit_simt_fallback(dtype):
+    # d not in {64,128} or N % 8 != 0 -> exact-math SIMT kernel with 16-bit I/O
+    for shape, dv in (((100, 32, 2), 32), ((77, 64, 1), 64)):
+        q, k, v = _qkv(shape, dv, dtype)
+        y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
+        y, l, m = fa.dense_fa(*(to_dev(t, dtype) for t in (q, k, v)))
+        assert fa.last_path() == "simt"
+        assert rel_err(to_np(y), y0) < 2e-3 and rel_err(to_np(l), l0) < 1e-4
+
+
+def test_dense_fwd_tc_large_logits_rescale():
+    # scores with a wide range so the lazy O-rescale path (threshold 2^8) is exercised
+    N, d, B = 1024, 64, 2
+    q, k, v = _qkv((N, d, B), d, BF16)
+    ramp = np.linspace(0.2, 6.0, N, dtype=np.float32)[:, None, None]          # later keys score higher
+    k = np.asfortranarray(torch.from_numpy(k * ramp).to(BF16).float().numpy())
+    q = np.asfortranarray(torch.from_numpy(q * 3).to(BF16).float().numpy())
+    y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
+    y, l, m = fa.dense_fa(*(to_dev(t, BF16) for t in (q, k, v)))
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(y), y0) < 4e-3         # P rounding dominates when one key takes all the mass
+    assert rel_err(np.log(to_np(l)) + to_np(m), np.log(l0) + m0) < 2e-3
+
+
+def test_dense_fwd_tc_full_size_sampled_rows():
+    """BASELINE config 3 geometry (N=8192, d=128, bf16) at a small batch: sampled rows against an
+    exact float64 evaluation, plus the size-independent property y(V=1) == 1."""
+    N, d, B = 8192, 128, 4
+    q, k, v = _qkv((N, d, B), d, BF16)
+    dq, dk, dv_ = (to_dev(t, BF16) for t in (q, k, v))
+    y, l, m = fa.dense_fa(dq, dk, dv_)
+    assert fa.last_path() == "tc"
+    rng = np.random.default_rng(7)
+    rows, bs = rng.integers(0, N, 48), rng.integers(0, B, 48)
+    o0, l0, m0 = sampled_dense_rows(q, k, v, rows, bs)
+    yy, ll, mm = to_np(y), to_np(l), to_np(m)
+    got = np.stack([yy[i, :, b] for i, b in zip(rows, bs)])
+    assert np.abs(got - o0).max() / np.abs(o0).max() < 2e-3
+    assert np.abs(np.array([ll[i, 0, b] for i, b in zip(rows, bs)]) / l0 - 1).max() < 2e-3
+    assert np.abs(np.array([mm[i, 0, b] for i, b in zip(rows, bs)]) - m0).max() < 2e-3
+    ones = fa.jl_empty((N, d, B), BF16).fill_(1)
+    y1, _, _ = fa.dense_fa(dq, dk, ones)
+    assert np.abs(to_np(y1) - 1).max() < 4e-3       # rows of P sum to 1 (bf16 output rounding)
+
+
+# ------------------------------------------------------------------------------- dense backward
+@pytest.mark.parametrize("shape,dv,dtype", [((30, 12, 2), 6, F32), ((300, 64, 2), 64, F32), ((129, 128, 2), 128, F32),
+                                            ((256, 64, 2), 64, BF16), ((200, 128, 1), 128, F16)])
+def test_dense_bwd(shape, dv, dtype):
+    q, k, v = _qkv(shape, dv, dtype)
+    g = randn_np(shape[:-2] + (dv, shape[-1]), 3, dtype)
+    dq0, dk0, dv0 = fo.dense_backward(*(t.astype(np.float64) for t in (q, k, v, g)))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.dense_fa(Q, K, V)
+    dq, dk, dvv = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    tol = tol_for(dtype) * (1 if dtype == F32 else 4)   # 16-bit: O, P and the outputs are all rounded
+    assert rel_err(to_np(dq), dq0) < tol
+    assert rel_err(to_np(dk), dk0) < tol
+    assert rel_err(to_np(dvv), dv0) < tol
+
+
+# ------------------------------------------------------------------------------- circulant
+@pytest.mark.parametrize("N,d,B,W", [(64, 8, 2, 9), (256, 32, 1, 129), (128, 16, 2, 16), (40, 4, 1, 40),
+                                     (700, 64, 1, 65), (1024, 64, 2, 255)])
+def test_circulant_fwd_fp32(N, d, B, W):
+    Q, K, V = _qkv((N, d, B), d, F32)
+    O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (Q, K, V)), W)
+    O, l, m = fa.circulant_fa(*(to_dev(t) for t in (Q, K, V)), W)
+    assert fa.last_path() == "simt"
+    assert rel_err(to_np(O), O0) < 1e-5 and rel_err(to_np(l), l0) < 1e-5 and rel_err(to_np(m), m0) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("N,d,B,W", [(1024, 64, 2, 255), (512, 128, 1, 129), (512, 64, 2, 64), (256, 64, 1, 256),
+                                     (384, 64, 1, 5), (2048, 64, 1, 1023), (128, 128, 2, 33)])
+def test_circulant_fwd_tc(N, d, B, W, dtype):
+    Q, K, V = _qkv((N, d, B), d, dtype)
+    O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (Q, K, V)), W)
+    O, l, m = fa.circulant_fa(*(to_dev(t, dtype) for t in (Q, K, V)), W)
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(O), O0) < 2e-3
+    assert rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
+
+
+@pytest.mark.parametrize("N,d,B,W,dtype", [(64, 8, 2, 9, F32), (128, 16, 2, 16, F32), (300, 64, 1, 65, F32),
+                                           (256, 64, 2, 33, BF16)])
+def test_circulant_bwd(N, d, B, W, dtype):
+    Q, K, V, G = (randn_np((N, d, B), s, dtype) for s in range(4))
+    dq0, dk0, dv0 = fo.circulant_backward(*(t.astype(np.float64) for t in (Q, K, V, G)), W)
+    q, k, v, g = (to_dev(t, dtype) for t in (Q, K, V, G))
+    O, l, m = fa.circulant_fa(q, k, v, W)
+    dq, dk, dvv = fa.circulant_fa_backward(q, k, v, O, g, l, m, W)
+    tol = tol_for(dtype) * (1 if dtype == F32 else 4)
+    assert rel_err(to_np(dq), dq0) < tol and rel_err(to_np(dk), dk0) < tol and rel_err(to_np(dvv), dv0) < tol
+
+
+def test_circulant_rejects_bad_window():
+    q = fa.jl_randn((16, 8, 1), 0)
+    with pytest.raises(fa.FaError):
+        fa.circulant_fa(q, q, q, 17)           # W > N would duplicate keys
+
+
+# ------------------------------------------------------------------------------- windowed
+WIN_CASES = [
+    ((64,), 16, dict(stride=16, pad=0)),          # block_fa
+    ((64,), 16, dict(stride=4, pad=0)),           # overlapping windows: fold-sum / count
+    ((22,), 5, dict(stride=5, pad=0)),            # 2 uncovered positions -> NaN
+    ((64,), 5, {}),                               # defaults stride=W, pad=2: 1 uncovered position
+    ((20, 12), 7, {}),                            # 2-D defaults (pad 3): zero-pad tokens in the softmax
+    ((16, 16), 3, dict(stride=1, pad=1)),         # sliding
+    ((6, 7, 8), 3, {}),                           # 3-D
+    ((8, 8, 8), 5, dict(stride=5, pad=1)),        # 3-D, 125 tokens / window (two 64-slot tiles)
+    ((200,), 70, dict(stride=35, pad=5)),         # window larger than one tile
+]
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("spatial,W,kws", WIN_CASES)
+def test_windowed_fwd(spatial, W, kws, dtype):
+    d, B = 8, 2
+    q, k, v = _qkv(spatial + (d, B), d, dtype)
+    y0, l0, m0 = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), W, **kws)
+    y, l, m = fa.windowed_fa(*(to_dev(t, dtype) for t in (q, k, v)), W, **kws)
+    tol = tol_for(dtype)
+    assert tuple(l.shape) == l0.shape
+    assert rel_err(to_np(y), y0) < tol             # includes the NaN pattern
+    assert rel_err(to_np(l), l0) < max(tol, 1e-5) and rel_err(to_np(m), m0) < max(tol, 1e-5)
+
+
+def test_windowed_fwd_config2_shape():
+    # BASELINE config 2: 64x64 image, 7x7 window, d=64, batch 8 (defaults: stride 7, pad 3)
+    q, k, v = _qkv((64, 64, 64, 8), 64, F32)
+    y0, l0, m0 = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), 7)
+    y, l, m = fa.windowed_fa(*(to_dev(t) for t in (q, k, v)), 7)
+    assert rel_err(to_np(y), y0) < 1e-5 and rel_err(to_np(l), l0) < 1e-5
+
+
+def test_block_fa_alias():
+    q, k, v = _qkv((64, 8, 2), 8, F32)
+    a = fa.block_fa(*(to_dev(t) for t in (q, k, v)), 16)
+    b = fa.windowed_fa(*(to_dev(t) for t in (q, k, v)), 16, stride=16, pad=0)
+    assert torch.equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("spatial,W,kws", [c for c in WIN_CASES if c[0] != (200,)] + [((150,), 70, dict(stride=35, pad=5))])
+def test_windowed_bwd(spatial, W, kws, dtype):
+    d, B = 8, 2
+    q, k, v = _qkv(spatial + (d, B), d, dtype)
+    g = randn_np(spatial + (d, B), 3, dtype)
+    dq0, dk0, dv0 = fo.windowed_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W, **kws)
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.windowed_fa(Q, K, V, W, **kws)
+    dq, dk, dvv = fa.windowed_fa_backward(Q, K, V, G, l, m, W, **kws)
+    tol = tol_for(dtype) * (1 if dtype == F32 else 4)
+    assert rel_err(to_np(dq), dq0) < tol and rel_err(to_np(dk), dk0) < tol and rel_err(to_np(dvv), dv0) < tol
+
+
+@pytest.mark.parametrize("spatial,W,kws", WIN_CASES[:8])
+def test_window_unwindow_bit_exact(spatial, W, kws):
+    x = randn_np(spatial + (3, 2), 5)
+    xw = fa.window(to_dev(x), W, **kws)
+    want = fo.window(x, W, kws.get("stride"), kws.get("pad"))
+    assert np.array_equal(to_np(xw), want.astype(np.float64))                 # pure data movement
+    Y = randn_np(want.shape, 6)
+    got = fa.unwindow(to_dev(Y), x.shape, W, **kws)
+    assert rel_err(to_np(got), fo.unwindow(Y.astype(np.float64), x.shape, W, kws.get("stride"), kws.get("pad"))) < 1e-6
+
+
+# ------------------------------------------------------------------------------- naive oracles (GPU-side)
+def test_naive_oracles_match_flash():
+    # test/test.jl:19-20 and bench/compare.jl:20,47,74, all on the device
+    q, k, v = (to_dev(t) for t in _qkv((96, 16, 2), 16, F32))
+    assert rel_err(to_np(fa.dense_fa(q, k, v)[0]), to_np(fa.dense_dpa(q, k, v)[0])) < 1e-5
+    assert rel_err(to_np(fa.circulant_fa(q, k, v, 9)[0]), to_np(fa.circulant_dpa(q, k, v, 9)[0])) < 1e-5
+    q, k, v = (to_dev(t) for t in _qkv((12, 10, 8, 2), 8, F32))
+    assert rel_err(to_np(fa.windowed_fa(q, k, v, 5, stride=2, pad=2)[0]),
+                   to_np(fa.windowed_dpa(q, k, v, 5, stride=2, pad=2)[0])) < 1e-5
+
+
+# ------------------------------------------------------------------------------- softmax
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(7, 9, 3), (1000, 33, 2), (64, 4096)])
+def test_fused_softmax(shape, dtype):
+    S = randn_np(shape, 0, dtype)
+    for dims in (1, 2):
+        want = fo.fused_softmax(S.astype(np.float64), dims)
+        got = fa.fused_softmax(to_dev(S, dtype), dims)
+        assert rel_err(to_np(got), want) < (1e-6 if dtype == F32 else 4e-3)
+    with pytest.raises(AssertionError):
+        fa.fused_softmax(to_dev(S, dtype), 3)
+
+
+# ------------------------------------------------------------------------------- host-buffer entry points
+def test_host_entry_points_match_device():
+    q, k, v = _qkv((300, 64, 5), 64, F32)
+    cq, ck, cv = (to_dev(t, F32, "cpu") for t in (q, k, v))
+    y_h, l_h, m_h = fa.dense_fa(cq, ck, cv)
+    assert not y_h.is_cuda
+    y_d, l_d, m_d = fa.dense_fa(*(to_dev(t) for t in (q, k, v)))
+    assert torch.equal(y_h, y_d.cpu()) and torch.equal(l_h, l_d.cpu())
+    O_h = fa.circulant_fa(cq, ck, cv, 33)[0]
+    assert torch.equal(O_h, fa.circulant_fa(*(to_dev(t) for t in (q, k, v)), 33)[0].cpu())
+    q, k, v = _qkv((20, 12, 8, 3), 8, F32)
+    yw_h = fa.windowed_fa(*(to_dev(t, F32, "cpu") for t in (q, k, v)), 7)[0]
+    yw_d = fa.windowed_fa(*(to_dev(t) for t in (q, k, v)), 7)[0]
+    assert torch.equal(yw_h.nan_to_num(7.0), yw_d.cpu().nan_to_num(7.0))

@@ -1,0 +1,57 @@
+"""Shared helpers for the parity tests."""
+import math
+
+import numpy as np
+import torch
+
+# BASELINE.md section 5 / BASELINE.json north_star: max-abs error relative to max-abs of the oracle
+TOL_FP32 = 1e-5      # exact-fp32 (TF32-off FFMA) path
+TOL_16 = 2e-3        # bf16 / fp16 compute with fp32 accumulation
+
+
+def randn_np(shape, seed, round_to=None):
+    """Seeded Float32 randn in Julia shape / Fortran order; optionally rounded so the values are
+    exactly representable in ``round_to`` (then GPU and oracle really see the same inputs)."""
+    x = np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+    if round_to is not None and round_to != torch.float32:
+        x = torch.from_numpy(x).to(round_to).float().numpy()
+    return np.asfortranarray(x)
+
+
+def to_dev(x, dtype=torch.float32, device="cuda"):
+    import fa_sm100a as fa
+    return fa.jl_array(x, dtype=dtype, device=device)
+
+
+def to_np(t):
+    return np.asfortranarray(t.detach().float().cpu().numpy().astype(np.float64))
+
+
+def rel_err(got, want):
+    """max|got-want| / max|want| over the finite entries; NaN patterns must coincide."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    ng, nw = np.isnan(got), np.isnan(want)
+    assert np.array_equal(ng, nw), f"NaN pattern differs: {ng.sum()} vs {nw.sum()}"
+    if nw.all():
+        return 0.0
+    scale = np.abs(want[~nw]).max()
+    return float(np.abs(got[~nw] - want[~nw]).max() / (scale if scale > 0 else 1.0))
+
+
+def tol_for(dtype):
+    return TOL_FP32 if dtype == torch.float32 else TOL_16
+
+
+def sampled_dense_rows(q, k, v, rows, batches):
+    """Exact float64 attention for a few (row, batch) pairs of a big problem: O(N d) each."""
+    d = q.shape[1]
+    out, ls, ms = [], [], []
+    for i, b in zip(rows, batches):
+        s = (k[:, :, b].astype(np.float64) @ q[i, :, b].astype(np.float64)) / math.sqrt(d)
+        m = s.max()
+        p = np.exp(s - m)
+        out.append((p / p.sum()) @ v[:, :, b].astype(np.float64))
+        ls.append(p.sum())
+        ms.append(m)
+    return np.array(out), np.array(ls), np.array(ms)
