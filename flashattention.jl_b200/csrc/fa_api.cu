@@ -27,7 +27,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
-             int lbo, int sbo, int kstep, int kbox, cudaStream_t st);
+             int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st);
 
 namespace {
 
@@ -455,10 +455,10 @@ int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, f
 // ------------------------------------------------------------------------------ diagnostics
 // One UMMA tile with caller-supplied descriptor fields (see fa_tc_probe.cu).  Not a product API.
 int fa_debug_umma_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
-                        int lbo, int sbo, int kstep, int kbox, void* stream) {
+                        int lbo, int sbo, int kstep, int kbox, int afmt, void* stream) {
   int rc = need_device();
   if (rc) return rc;
-  return tc_probe(mode, a, b, p, out, D, dtype, lbo, sbo, kstep, kbox, static_cast<cudaStream_t>(stream));
+  return tc_probe(mode, a, b, p, out, D, dtype, lbo, sbo, kstep, kbox, afmt, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

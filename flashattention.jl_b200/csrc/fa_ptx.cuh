@@ -156,10 +156,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
-// kind::f16 instruction descriptor: fp32 accumulate, A/B format (0 = f16, 1 = bf16),
+// kind::f16 instruction descriptor: fp32 accumulate, independent A and B formats (0 = f16, 1 = bf16),
 // a_major / b_major (0 = K-major, 1 = MN-major), N >> 3, M >> 4.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int ab_format, int a_mn_major, int b_mn_major, int M, int N) {
-  return (1u << 4) | ((uint32_t)ab_format << 7) | ((uint32_t)ab_format << 10) |
+__host__ __device__ constexpr uint32_t make_idesc_f16(int a_format, int b_format, int a_mn_major, int b_mn_major, int M, int N) {
+  return (1u << 4) | ((uint32_t)a_format << 7) | ((uint32_t)b_format << 10) |
          ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }

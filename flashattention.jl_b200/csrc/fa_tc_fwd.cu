@@ -97,9 +97,7 @@ __device__ __forceinline__ void tile_ranges(const TcParams& prm, int q0, int& kb
   }
 }
 
-template <int FMT>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (FMT == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
@@ -173,8 +171,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       }
     } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc_f16(FMT, 1, 1, 128, 128);   // A, B MN-major
-      constexpr uint32_t idesc_pv = make_idesc_f16(FMT, 0, 0, 128, D);     // A in TMEM, B K-major
+      constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);   // A, B MN-major
+      // P is always fp16 (values in [0, 2^8], 11-bit significand) even when V is bf16
+      constexpr uint32_t idesc_pv = make_idesc_f16(0, FMT, 0, 0, 128, D);       // A in TMEM, B K-major
       const uint32_t colS[2] = {tmem_base + C::COL_S0, tmem_base + C::COL_S1};
       const uint32_t colO[2] = {tmem_base + C::COL_O0, tmem_base + C::COL_O1};
       uint32_t pphase[2] = {0, 0};
@@ -287,7 +286,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             const float p0 = ex2(fmaf(__uint_as_float(s[c][i]), scale, neg_m));
             const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), scale, neg_m));
             sum0 += p0; sum1 += p1;
-            pk[i >> 1] = pack2<FMT>(p0, p1);
+            pk[i >> 1] = pack_half2(p0, p1);
           }
           tmem_st16(tS + 16 * c, pk);
         }

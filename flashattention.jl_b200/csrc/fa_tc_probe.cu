@@ -15,7 +15,8 @@ using namespace ptx;
 struct ProbeParams {
   int mode;         // 0: S = A^T B (both MN-major from smem);  1: O = P V (P in TMEM, V K-major smem)
   int D;            // channels (64 or 128)
-  int fmt;          // 0 f16, 1 bf16
+  int fmt;          // 0 f16, 1 bf16 (smem operands)
+  int afmt;         // mode 1: format of P in TMEM (0 f16, 1 bf16)
   int lbo, sbo;     // descriptor byte offsets for the smem operands
   int kstep;        // byte advance of the start address per K=16 step (within a 64-wide box)
   int kbox;         // k-steps per box before jumping by box_bytes (mode 1); 0 = never
@@ -53,7 +54,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float a = pr[32 * c + 2 * i], b = pr[32 * c + 2 * i + 1];
-        if (prm.fmt == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
+        if (prm.afmt == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
         else { __half2 h = __floats2half2_rn(a, b); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
       }
       tmem_st16(tmem_base + lane_addr + 16 * c, pk);
@@ -76,14 +77,14 @@ probe_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
     mbar_wait(bars, 0);
     tc_fence_after();
     if (prm.mode == 0) {
-      const uint32_t idesc = make_idesc_f16(prm.fmt, 1, 1, 128, 128);
+      const uint32_t idesc = make_idesc_f16(prm.fmt, prm.fmt, 1, 1, 128, 128);
       for (int ks = 0; ks < D / 16; ++ks) {
         const uint64_t ad = make_smem_desc_sw128(sA + ks * prm.kstep, prm.lbo, prm.sbo);
         const uint64_t bd = make_smem_desc_sw128(sB + ks * prm.kstep, prm.lbo, prm.sbo);
         mma_ss(tmem_base + 128, ad, bd, idesc, ks > 0);
       }
     } else {
-      const uint32_t idesc = make_idesc_f16(prm.fmt, 0, 0, 128, D);
+      const uint32_t idesc = make_idesc_f16(prm.afmt, prm.fmt, 0, 0, 128, D);
       for (int ks = 0; ks < 8; ++ks) {
         const uint32_t off = prm.kbox ? (ks / prm.kbox) * box + (ks % prm.kbox) * prm.kstep : ks * prm.kstep;
         const uint64_t bd = make_smem_desc_sw128(sB + off, prm.lbo, prm.sbo);
@@ -112,13 +113,13 @@ probe_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
 }  // namespace
 
 int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
-             int lbo, int sbo, int kstep, int kbox, cudaStream_t st) {
+             int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st) {
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap_public(&ta, a ? a : b, dtype, 128, D, 1))) return rc;
   if ((rc = make_tmap_public(&tb, b, dtype, 128, D, 1))) return rc;
   ProbeParams prm;
-  prm.mode = mode; prm.D = D; prm.fmt = dtype == FA_BF16 ? 1 : 0;
+  prm.mode = mode; prm.D = D; prm.fmt = dtype == FA_BF16 ? 1 : 0; prm.afmt = afmt < 0 ? prm.fmt : afmt;
   prm.lbo = lbo; prm.sbo = sbo; prm.kstep = kstep; prm.kbox = kbox; prm.p = p; prm.out = out;
   const int smem = 4 * 64 * D * 2 + 64 + 1024;
   FA_CUDA_TRY(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -80,7 +80,7 @@ def _load():
         "fa_dense_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, ci]),
         "fa_circulant_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, i64, ci, ci, ci]),
         "fa_windowed_fwd_host": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, ci]),
-        "fa_debug_umma_probe": (ci, [ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+        "fa_debug_umma_probe": (ci, [ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)          # AttributeError here == header/library mismatch

@@ -5,6 +5,10 @@ bench/compare.jl:20,47,74, plus backward and the edge cases of SURV
 
 Tolerances (BASELINE.json north_star): 1e-5 for the exact-fp32 path, 2e-3 for bf16/fp16
 compute with fp32 accumulation; both as max-abs error relative to max-abs of the oracle.
+16-bit cases feed GPU and oracle the same Float32 values (pre-rounded so they are exactly
+representable), and results that are STORED in a 16-bit type are allowed that type's own
+round-to-nearest half-ulp on top of the compute tolerance (util.rel_err, `storage=`): bf16
+storage alone can be off by 2^-8 = 3.9e-3, which no kernel can avoid.
 """
 import numpy as np
 import pytest
@@ -59,7 +63,7 @@ def test_dense_fwd_tc(N, d, B, dtype):
     y, l, m = fa.dense_fa(*(to_dev(t, dtype) for t in (q, k, v)))
     assert fa.last_path() == "tc"
     assert y.dtype == dtype and l.dtype == torch.float32
-    assert rel_err(to_np(y), y0) < 2e-3
+    assert rel_err(to_np(y), y0, dtype) < 2e-3
     assert rel_err(to_np(l), l0) < 2e-3
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
 
@@ -72,7 +76,7 @@ def test_dense_fwd_16bit_simt_fallback(dtype):
         y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
         y, l, m = fa.dense_fa(*(to_dev(t, dtype) for t in (q, k, v)))
         assert fa.last_path() == "simt"
-        assert rel_err(to_np(y), y0) < 2e-3 and rel_err(to_np(l), l0) < 1e-4
+        assert rel_err(to_np(y), y0, dtype) < 1e-5 and rel_err(to_np(l), l0) < 1e-4
 
 
 def test_dense_fwd_tc_large_logits_rescale():
@@ -85,7 +89,7 @@ def test_dense_fwd_tc_large_logits_rescale():
     y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
     y, l, m = fa.dense_fa(*(to_dev(t, BF16) for t in (q, k, v)))
     assert fa.last_path() == "tc"
-    assert rel_err(to_np(y), y0) < 4e-3         # P rounding dominates when one key takes all the mass
+    assert rel_err(to_np(y), y0, BF16) < 2e-3
     assert rel_err(np.log(to_np(l)) + to_np(m), np.log(l0) + m0) < 2e-3
 
 
@@ -102,12 +106,12 @@ def test_dense_fwd_tc_full_size_sampled_rows():
     o0, l0, m0 = sampled_dense_rows(q, k, v, rows, bs)
     yy, ll, mm = to_np(y), to_np(l), to_np(m)
     got = np.stack([yy[i, :, b] for i, b in zip(rows, bs)])
-    assert np.abs(got - o0).max() / np.abs(o0).max() < 2e-3
+    assert rel_err(got, o0, BF16) < 2e-3
     assert np.abs(np.array([ll[i, 0, b] for i, b in zip(rows, bs)]) / l0 - 1).max() < 2e-3
     assert np.abs(np.array([mm[i, 0, b] for i, b in zip(rows, bs)]) - m0).max() < 2e-3
     ones = fa.jl_empty((N, d, B), BF16).fill_(1)
     y1, _, _ = fa.dense_fa(dq, dk, ones)
-    assert np.abs(to_np(y1) - 1).max() < 4e-3       # rows of P sum to 1 (bf16 output rounding)
+    assert np.abs(to_np(y1) - 1).max() < 2e-3       # rows of P sum to 1 (1.0 is exact in bf16)
 
 
 # ------------------------------------------------------------------------------- dense backward
@@ -120,10 +124,10 @@ def test_dense_bwd(shape, dv, dtype):
     Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
     y, l, m = fa.dense_fa(Q, K, V)
     dq, dk, dvv = fa.dense_fa_backward(Q, K, V, y, G, l, m)
-    tol = tol_for(dtype) * (1 if dtype == F32 else 4)   # 16-bit: O, P and the outputs are all rounded
-    assert rel_err(to_np(dq), dq0) < tol
-    assert rel_err(to_np(dk), dk0) < tol
-    assert rel_err(to_np(dvv), dv0) < tol
+    tol = tol_for(dtype)
+    assert rel_err(to_np(dq), dq0, dtype) < tol
+    assert rel_err(to_np(dk), dk0, dtype) < tol
+    assert rel_err(to_np(dvv), dv0, dtype) < tol
 
 
 # ------------------------------------------------------------------------------- circulant
@@ -145,7 +149,7 @@ def test_circulant_fwd_tc(N, d, B, W, dtype):
     O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (Q, K, V)), W)
     O, l, m = fa.circulant_fa(*(to_dev(t, dtype) for t in (Q, K, V)), W)
     assert fa.last_path() == "tc"
-    assert rel_err(to_np(O), O0) < 2e-3
+    assert rel_err(to_np(O), O0, dtype) < 2e-3
     assert rel_err(to_np(l), l0) < 2e-3
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
 
@@ -158,8 +162,8 @@ def test_circulant_bwd(N, d, B, W, dtype):
     q, k, v, g = (to_dev(t, dtype) for t in (Q, K, V, G))
     O, l, m = fa.circulant_fa(q, k, v, W)
     dq, dk, dvv = fa.circulant_fa_backward(q, k, v, O, g, l, m, W)
-    tol = tol_for(dtype) * (1 if dtype == F32 else 4)
-    assert rel_err(to_np(dq), dq0) < tol and rel_err(to_np(dk), dk0) < tol and rel_err(to_np(dvv), dv0) < tol
+    tol = tol_for(dtype)
+    assert rel_err(to_np(dq), dq0, dtype) < tol and rel_err(to_np(dk), dk0, dtype) < tol and rel_err(to_np(dvv), dv0, dtype) < tol
 
 
 def test_circulant_rejects_bad_window():
@@ -191,7 +195,7 @@ def test_windowed_fwd(spatial, W, kws, dtype):
     y, l, m = fa.windowed_fa(*(to_dev(t, dtype) for t in (q, k, v)), W, **kws)
     tol = tol_for(dtype)
     assert tuple(l.shape) == l0.shape
-    assert rel_err(to_np(y), y0) < tol             # includes the NaN pattern
+    assert rel_err(to_np(y), y0, dtype) < tol      # includes the NaN pattern
     assert rel_err(to_np(l), l0) < max(tol, 1e-5) and rel_err(to_np(m), m0) < max(tol, 1e-5)
 
 
@@ -220,8 +224,8 @@ def test_windowed_bwd(spatial, W, kws, dtype):
     Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
     y, l, m = fa.windowed_fa(Q, K, V, W, **kws)
     dq, dk, dvv = fa.windowed_fa_backward(Q, K, V, G, l, m, W, **kws)
-    tol = tol_for(dtype) * (1 if dtype == F32 else 4)
-    assert rel_err(to_np(dq), dq0) < tol and rel_err(to_np(dk), dk0) < tol and rel_err(to_np(dvv), dv0) < tol
+    tol = tol_for(dtype)
+    assert rel_err(to_np(dq), dq0, dtype) < tol and rel_err(to_np(dk), dk0, dtype) < tol and rel_err(to_np(dvv), dv0, dtype) < tol
 
 
 @pytest.mark.parametrize("spatial,W,kws", WIN_CASES[:8])
@@ -254,7 +258,7 @@ def test_fused_softmax(shape, dtype):
     for dims in (1, 2):
         want = fo.fused_softmax(S.astype(np.float64), dims)
         got = fa.fused_softmax(to_dev(S, dtype), dims)
-        assert rel_err(to_np(got), want) < (1e-6 if dtype == F32 else 4e-3)
+        assert rel_err(to_np(got), want, dtype) < 1e-5
     with pytest.raises(AssertionError):
         fa.fused_softmax(to_dev(S, dtype), 3)
 

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import fa_sm100a as fa  # noqa: E402
 
 
-def run(mode, D, dtype, lbo, sbo, kstep, kbox):
+def run(mode, D, dtype, lbo, sbo, kstep, kbox, afmt=-1):
     torch.manual_seed(0)
     code = fa.FA_BF16 if dtype == torch.bfloat16 else fa.FA_F16
     a = torch.randn(D, 128, device="cuda").to(dtype)          # [D][tokens]  (token contiguous)
@@ -25,12 +25,13 @@ def run(mode, D, dtype, lbo, sbo, kstep, kbox):
         want = a.double().T @ b.double()
         p = None
     else:
-        p = torch.rand(128, 128, device="cuda").to(dtype).float().contiguous()
+        pdt = dtype if afmt < 0 else (torch.bfloat16 if afmt == 1 else torch.float16)
+        p = torch.rand(128, 128, device="cuda").to(pdt).float().contiguous()
         out = torch.zeros(128, D, device="cuda")
         want = p.double() @ b.double().T                           # O[i][c] = sum_j P[i][j] V[c][j]
     rc = fa.lib.fa_debug_umma_probe(mode, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
                                     None if p is None else ctypes.c_void_p(p.data_ptr()),
-                                    ctypes.c_void_p(out.data_ptr()), D, code, lbo, sbo, kstep, kbox, None)
+                                    ctypes.c_void_p(out.data_ptr()), D, code, lbo, sbo, kstep, kbox, afmt, None)
     if rc != 0:
         return f"rc={rc} {fa.lib.fa_last_error_string().decode()}"
     torch.cuda.synchronize()
@@ -53,6 +54,7 @@ def main():
                          "lbo=16 sbo=1024 kstep=32 kbox=0": (16, 1024, 32, 0)}
             for name, (lbo, sbo, ks, kb) in variants1.items():
                 print(f"  PV  {name:45s} rel_err={run(1, D, dtype, lbo, sbo, ks, kb)}")
+            print(f"  PV  mixed: P fp16 in TMEM x V {dtype}            rel_err={run(1, D, dtype, 16, 1024, 32, 4, afmt=0)}")
 
 
 if __name__ == "__main__":
