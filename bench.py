@@ -77,18 +77,18 @@ class ClockSampler:
 
 
 def cpu_reference_tflops(steps, warmup, batch_sample):
-    """CPU restatement of the reference (oracle port; the Julia reference cannot run here) on a
-    bounded sample of the workload: Float32, same N and d, `batch_sample` batch elements, all host
-    cores as the reference's `@threads` would use (src/dense.jl:45)."""
+    """CPU restatement of the reference (oracle/fa_oracle.c, C + OpenMP; the Julia reference cannot
+    run here) on a bounded sample of the workload: Float32, same N and d, `batch_sample` batch
+    elements, all host cores as the reference's `@threads` would use (src/dense.jl:45)."""
     import numpy as np
-    from oracle import fa_oracle as fo
-    cores = os.cpu_count() or 1
+    from oracle import c_oracle as co
+    cores = co.threads()
     rng = np.random.default_rng(0)
     q, k, v = (np.asfortranarray(rng.standard_normal((N, D, batch_sample), dtype=np.float32)) for _ in range(3))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        fo.dense_fa(q, k, v, threads=cores)
+        co.dense_fa(q, k, v)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
@@ -100,7 +100,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 4
+    sample_b = 8
     val, t, cores = cpu_reference_tflops(args.steps, args.warmup, sample_b)
     line = {
         "impl": "reference", "metric": "dense_fa forward attention TFLOP/s (4*N^2*d*B / time)", "value": val,
@@ -109,8 +109,8 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic randn (seeded)",
         "config": {"workload": WORKLOAD, "sample": f"B={sample_b} of {B_PER_GPU} batch elements per step, Float32"},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle dense_fa (numpy restatement of src/dense.jl:21-102), N={N} d={D} B={sample_b}, "
-                                   f"{cores} threads over (batch,row-block) tasks"},
+                         "sample": f"oracle/fa_oracle.c dense_fa (C+OpenMP restatement of src/dense.jl:21-102), N={N} d={D} B={sample_b}, "
+                                   f"{cores} OpenMP threads over (batch,row-block) tasks"},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "tokens_per_s": sample_b * N / t,
     }
@@ -241,9 +241,9 @@ def main():
             "gpu_launches": args.steps, "clocks": clocks, "roofline": roof, "e2e": e2e,
         }
         if not args.no_cpu:
-            cv, ct, cores = cpu_reference_tflops(1, 1, 2)
+            cv, ct, cores = cpu_reference_tflops(2, 1, 8)
             line["cpu_baseline"] = {"value": cv, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle dense_fa Float32 N={N} d={D} B=2 ({ct:.2f} s/step), {cores} threads; "
+                                    "sample": f"oracle/fa_oracle.c dense_fa Float32 N={N} d={D} B=8 ({ct:.2f} s/step), {cores} OpenMP threads; "
                                               "CPU restatement of reference (Julia runtime unavailable)"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -89,6 +89,15 @@ static void gemm_pv(float* restrict On, const float* restrict P, const float* re
   }
 }
 
+/* p[c] = exp(p[c] - mij), returns the row sum (src/dense.jl:79-80).  All arguments are finite here,
+ * so this one helper may use the vector math library (libmvec) through fast-math codegen. */
+static float __attribute__((optimize("-ffast-math"), noinline)) exp_row(float* restrict p, long n, float mij) {
+  float s = 0.f;
+#pragma omp simd reduction(+ : s)
+  for (long c = 0; c < n; ++c) { p[c] = expf(p[c] - mij); s += p[c]; }
+  return s;
+}
+
 /* dense_fa!(O,l,m,Q,K,V)  src/dense.jl:21-102.  ldn = token stride between channels (N for a
  * plain (N,d,B) array), bstride_* = elements between batch elements. */
 static void dense_fwd_core(const float* Q, const float* K, const float* V, float* O, float* l, float* m,
@@ -120,9 +129,7 @@ static void dense_fwd_core(const float* Q, const float* K, const float* V, float
             float* p = Pij + r * bc;
             float mij = -INFINITY;
             for (long c = 0; c < bc; ++c) mij = p[c] > mij ? p[c] : mij;               /* :78 */
-            float lij = 0.f;
-#pragma omp simd reduction(+ : lij)
-            for (long c = 0; c < bc; ++c) { p[c] = expf(p[c] - mij); lij += p[c]; }   /* :79-80 */
+            const float lij = exp_row(p, bc, mij);                                     /* :79-80 */
             const float mnew = mi[r] > mij ? mi[r] : mij;                              /* :82 */
             const float ei = expf(mi[r] - mnew), eij = expf(mij - mnew);               /* :83-84 */
             const float lnew = ei * li[r] + eij * lij;                                 /* :85 */
