@@ -97,7 +97,9 @@ __device__ __forceinline__ void tile_ranges(const TcParams& prm, int q0, int& kb
   }
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (FMT == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
@@ -172,8 +174,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     } else if (warp == 1 && lane == 0) {
       // ------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);   // A, B MN-major
-      // P is always fp16 (values in [0, 2^8], 11-bit significand) even when V is bf16
-      constexpr uint32_t idesc_pv = make_idesc_f16(0, FMT, 0, 0, 128, D);       // A in TMEM, B K-major
+      // P takes the input format: mixing A = f16 with B = bf16 in one kind::f16 MMA raises
+      // "illegal instruction" on sm_100a (measured, round 1), so bf16 inputs mean bf16 P.
+      constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);     // A in TMEM, B K-major
       const uint32_t colS[2] = {tmem_base + C::COL_S0, tmem_base + C::COL_S1};
       const uint32_t colO[2] = {tmem_base + C::COL_O0, tmem_base + C::COL_O1};
       uint32_t pphase[2] = {0, 0};
@@ -286,7 +289,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             const float p0 = ex2(fmaf(__uint_as_float(s[c][i]), scale, neg_m));
             const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), scale, neg_m));
             sum0 += p0; sum1 += p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+            pk[i >> 1] = pack2<FMT>(p0, p1);
           }
           tmem_st16(tS + 16 * c, pk);
         }

@@ -1,0 +1,26 @@
+# FlashAttention.jl host layer over libfa_sm100a.so  (UNVERIFIED HERE: no Julia runtime in the build
+# image; the Python ctypes harness fa_sm100a/__init__.py binds the same symbols 1:1 and is what
+# the tests exercise).  Export list identical to the reference (src/FlashAttention.jl:13,20-21,26-27).
+module FlashAttention
+
+using Libdl
+using LinearAlgebra, SparseArrays
+using NNlib, MLUtils
+using CUDA
+
+include("libfa.jl")          # library handle, dtype codes, status -> error()
+include("utils.jl")          # cartesian_circulant, circulant, window, unwindow   (reference src/utils.jl)
+include("fused_softmax.jl")
+export fused_softmax, fused_softmax!
+
+include("naive.jl")          # dense_dpa, windowed_dpa, circulant_dpa: the naive oracles, kept naive
+export dense_dpa!, circulant_dpa!
+export dense_dpa, windowed_dpa, circulant_dpa, block_dpa
+
+include("dense.jl")
+include("windowed.jl")
+include("circulant.jl")
+export dense_fa!, circulant_fa!
+export dense_fa, windowed_fa, circulant_fa, block_fa
+
+end

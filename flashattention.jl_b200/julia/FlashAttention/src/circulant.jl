@@ -1,0 +1,52 @@
+# circulant_fa / circulant_fa! -- reference src/circulant.jl:1,9.  The reference's allocating
+# wrapper forgets to pass W (src/circulant.jl:6, a MethodError); this one passes it.
+@inline function circulant_fa(Q, K, V, W)
+    N, d, batchsize = size(Q)
+    O = similar(Q, N, size(V, 2), batchsize)
+    l = statarray(Q, N, 1, batchsize)
+    m = statarray(Q, N, 1, batchsize)
+    return circulant_fa!(O, l, m, Q, K, V, W)
+end
+
+function circulant_fa!(O::CuArray{T, 3}, l::CuArray{Float32, 3}, m::CuArray{Float32, 3},
+                       Q::CuArray{T, 3}, K::CuArray{T, 3}, V::CuArray{T, 3}, W::Int; flags::Integer=0) where {T}
+    N, d, batchsize = size(Q)
+    rc = ccall(sym(:fa_circulant_fwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}),
+               devptr(Q), devptr(K), devptr(V), devptr(O), devptr(l), devptr(m),
+               N, d, size(V, 2), batchsize, W, fa_dtype(T), Cint(flags), current_stream())
+    check(rc, "fa_circulant_fwd")
+    return O, l, m
+end
+
+function circulant_fa!(O::Array{T, 3}, l::Array{Float32, 3}, m::Array{Float32, 3},
+                       Q::Array{T, 3}, K::Array{T, 3}, V::Array{T, 3}, W::Int; flags::Integer=0, device::Integer=0) where {T}
+    N, d, batchsize = size(Q)
+    rc = ccall(sym(:fa_circulant_fwd_host), Cint,
+               (Ptr{T}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{Float32}, Ptr{Float32},
+                Int64, Int64, Int64, Int64, Int64, Cint, Cint, Cint),
+               Q, K, V, O, l, m, N, d, size(V, 2), batchsize, W, fa_dtype(T), Cint(flags), Cint(device))
+    check(rc, "fa_circulant_fwd_host")
+    return O, l, m
+end
+
+function circulant_fa_backward(Q::CuArray{T, 3}, K::CuArray{T, 3}, V::CuArray{T, 3}, O::CuArray{T, 3},
+                               dO::CuArray{T, 3}, l::CuArray{Float32, 3}, m::CuArray{Float32, 3}, W::Int;
+                               flags::Integer=0) where T
+    N, d, batchsize = size(Q)
+    dv = size(V, 2)
+    dQ, dK, dV = similar(Q), similar(K), similar(V)
+    nws = ccall(sym(:fa_workspace_bytes_circulant_bwd), Csize_t, (Int64, Int64, Int64, Int64, Int64, Cint, Cint),
+                N, d, dv, batchsize, W, fa_dtype(T), Cint(flags))
+    ws = CuArray{UInt8}(undef, max(nws, 256))
+    rc = ccall(sym(:fa_circulant_bwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Cint, Cint,
+                Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+               devptr(Q), devptr(K), devptr(V), devptr(O), devptr(dO), devptr(l), devptr(m),
+               devptr(dQ), devptr(dK), devptr(dV), N, d, dv, batchsize, W, fa_dtype(T), Cint(flags),
+               devptr(ws), length(ws), current_stream())
+    check(rc, "fa_circulant_bwd")
+    return dQ, dK, dV
+end

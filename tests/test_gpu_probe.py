@@ -16,4 +16,3 @@ def test_umma_descriptor_conventions(D, dtype):
     box = 64 * D * 2
     assert probe_umma.run(0, D, dtype, box, 1024, 2048, 0) < 1e-5     # S = Q K^T, MN-major SW128
     assert probe_umma.run(1, D, dtype, 16, 1024, 32, 4) < 1e-5        # O = P V,  P in TMEM, V K-major SW128
-    assert probe_umma.run(1, D, dtype, 16, 1024, 32, 4, afmt=0) < 1e-5   # mixed formats: P fp16 x V bf16/fp16

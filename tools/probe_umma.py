@@ -54,7 +54,6 @@ def main():
                          "lbo=16 sbo=1024 kstep=32 kbox=0": (16, 1024, 32, 0)}
             for name, (lbo, sbo, ks, kb) in variants1.items():
                 print(f"  PV  {name:45s} rel_err={run(1, D, dtype, lbo, sbo, ks, kb)}")
-            print(f"  PV  mixed: P fp16 in TMEM x V {dtype}            rel_err={run(1, D, dtype, 16, 1024, 32, 4, afmt=0)}")
 
 
 if __name__ == "__main__":
