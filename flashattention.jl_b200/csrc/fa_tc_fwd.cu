@@ -14,14 +14,23 @@
 //       (rows = channel, K = key contiguous; SBO = 1024 B per 8 channels).
 // No transposes, no staging copies: the transposed Julia layout maps 1:1 onto UMMA descriptors.
 //
-// CTA = 384 threads, one CTA per SM (512 TMEM columns):
-//   warp 0      TMA producer (Q pair once; K and V tiles through two mbarrier rings)
-//   warp 1      MMA issuer   (single thread; S_t = Q_t K_j^T, O_t += P_t V_j, ping-pong t = 0,1)
+// CTA = 384 threads, one CTA per SM (512 TMEM columns), a pair of 128-query tiles t = 0,1:
+//   warp 0      TMA producer (Q pair once; 64-key K and V tiles through two mbarrier rings)
+//   warps 1, 3  MMA issuers  (one thread per Q tile t; the tiles are independent, and one thread
+//               cannot issue 24 small MMAs per 1024-cycle step): at global step g, for its t:
+//                   O_t += P_t(g-2) V(g-2)      (A = P from TMEM, B = V K-major from smem)
+//                   S_t[g&1] = Q_t K(g)^T       (A, B MN-major from smem, N = 64)
+//               i.e. QK runs TWO steps ahead of PV into a double-buffered S, so the softmax
+//               warps never wait for the tensor pipe and the tensor pipe never waits for more
+//               than one softmax (v1 had one S buffer per tile: softmax(j) and [PV(j), QK(j+1)]
+//               of a tile were serialized, tensor pipe 53 % -- profiles/r1a_*).
 //   warp 2      TMEM allocator
 //   warps 4-7   softmax for Q tile 0   (thread == row; S row read from TMEM with tcgen05.ld,
 //   warps 8-11  softmax for Q tile 1    running max/sum in registers, exp2, P written back to
-//                                       TMEM as 16-bit, lazy O rescale, final O/l, m epilogue)
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+d) O1 [256+d,256+2d); P_t aliases S_t.
+//                                       TMEM as 16-bit over its own S buffer, lazy O rescale,
+//                                       final O/l, m epilogue)
+// TMEM columns: S_t[b] at 128 t + 64 b (64 fp32 columns each), O_t at 256 + d t; P_t(j) aliases
+// the first 32 columns of S_t[j&1].
 #include <cuda.h>
 #include "fa_common.cuh"
 #include "fa_ptx.cuh"
@@ -32,32 +41,35 @@ namespace {
 using namespace ptx;
 
 constexpr int TC_THREADS = 384;
+constexpr int BN = 64;                      // keys per K/V tile (one TMA box)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // lazy rescale: P may grow to 2^8 before O is rescaled
 
 template <int D>
 struct Cfg {
-  static constexpr int KV_STAGES = (D == 128) ? 2 : 4;
+  static constexpr int K_STAGES = (D == 128) ? 3 : 4;
+  static constexpr int V_STAGES = (D == 128) ? 4 : 6;
   static constexpr int BOX_BYTES = 64 * D * 2;          // 64 tokens x D channels, 16-bit
-  static constexpr int TILE_BYTES = 2 * BOX_BYTES;      // 128 tokens
+  static constexpr int QTILE_BYTES = 2 * BOX_BYTES;     // 128 queries
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = 2 * TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
+  static constexpr int OFF_K = 2 * QTILE_BYTES;
+  static constexpr int OFF_V = OFF_K + K_STAGES * BOX_BYTES;
+  static constexpr int OFF_BAR = OFF_V + V_STAGES * BOX_BYTES;
   // barrier slots (8 B each)
-  static constexpr int BAR_QFULL = 0;                    // [2]
-  static constexpr int BAR_KFULL = 2;                    // [KV_STAGES]
-  static constexpr int BAR_KEMPTY = BAR_KFULL + KV_STAGES;
-  static constexpr int BAR_VFULL = BAR_KEMPTY + KV_STAGES;
-  static constexpr int BAR_VEMPTY = BAR_VFULL + KV_STAGES;
-  static constexpr int BAR_SFULL = BAR_VEMPTY + KV_STAGES;   // [2]
-  static constexpr int BAR_PFULL = BAR_SFULL + 2;            // [2]
-  static constexpr int BAR_OFINAL = BAR_PFULL + 2;           // [2]
+  static constexpr int BAR_QFULL = 0;                          // [2]
+  static constexpr int BAR_KFULL = 2;                          // [K_STAGES]
+  static constexpr int BAR_KEMPTY = BAR_KFULL + K_STAGES;
+  static constexpr int BAR_VFULL = BAR_KEMPTY + K_STAGES;      // [V_STAGES]
+  static constexpr int BAR_VEMPTY = BAR_VFULL + V_STAGES;
+  static constexpr int BAR_SFULL = BAR_VEMPTY + V_STAGES;      // [2 tiles][2 buffers]
+  static constexpr int BAR_PFULL = BAR_SFULL + 4;              // [2][2]
+  static constexpr int BAR_ODONE = BAR_PFULL + 4;              // [2]  one completion per PV_t
+  static constexpr int BAR_OFINAL = BAR_ODONE + 2;             // [2]  single use: all MMAs of tile t done
   static constexpr int NUM_BARS = BAR_OFINAL + 2;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;   // + alignment slack
-  static constexpr int COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 256 + D;
+  static constexpr int COL_S = 0, COL_O = 256;                   // S_t[b] = 128 t + 64 b; O_t = 256 + D t
 };
 
 struct TcParams {
@@ -72,23 +84,23 @@ __host__ __device__ inline int floor_div(int a, int b) { return (a >= 0) ? a / b
 
 struct TileRange { int jlo, jhi; };
 
-// key-tile stream of one CTA (a pair of 128-query tiles starting at q0)
+// key-tile stream of one CTA (a pair of 128-query tiles starting at q0), in 64-key tiles
 __device__ __forceinline__ void tile_ranges(const TcParams& prm, int q0, int& kbase, int& nj, TileRange (&tr)[2]) {
   if (prm.mode == MODE_CIRCULANT) {
-    kbase = floor_div(q0 - prm.p, 128) * 128;
+    kbase = floor_div(q0 - prm.p, BN) * BN;
     nj = 0;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int i0 = q0 + 128 * t;
       if (i0 < prm.N) {
-        tr[t].jlo = floor_div(i0 - prm.p - kbase, 128);
-        tr[t].jhi = floor_div(i0 + 127 - prm.p + prm.W - 1 - kbase, 128) + 1;
+        tr[t].jlo = floor_div(i0 - prm.p - kbase, BN);
+        tr[t].jhi = floor_div(i0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1;
         nj = tr[t].jhi > nj ? tr[t].jhi : nj;
       } else { tr[t].jlo = 0; tr[t].jhi = 0; }
     }
   } else {
     kbase = 0;
-    nj = (prm.N + 127) / 128;
+    nj = (prm.N + BN - 1) / BN;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       tr[t].jlo = 0;
@@ -124,15 +136,11 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) mbar_init(bar(C::BAR_QFULL + i), 1);
-    for (int i = 0; i < C::KV_STAGES; ++i) {
-      mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), 1);
-      mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(C::BAR_SFULL + i), 1);
-      mbar_init(bar(C::BAR_PFULL + i), 128);
-      mbar_init(bar(C::BAR_OFINAL + i), 1);
-    }
+    // K/V slots are released by BOTH MMA issuers (count 2)
+    for (int i = 0; i < C::K_STAGES; ++i) { mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), 2); }
+    for (int i = 0; i < C::V_STAGES; ++i) { mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), 2); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar(C::BAR_SFULL + i), 1); mbar_init(bar(C::BAR_PFULL + i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(C::BAR_ODONE + i), 1); mbar_init(bar(C::BAR_OFINAL + i), 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -147,131 +155,147 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
   tile_ranges(prm, q0, kbase, nj, tr);
 
   if (warp < 4) {
-    setmaxnreg_dec<48>();
+    setmaxnreg_dec<64>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         if (tr[t].jhi > tr[t].jlo) {
-          mbar_arrive_expect_tx(bar(C::BAR_QFULL + t), C::TILE_BYTES);
-          tma_load_3d(sQ + t * C::TILE_BYTES, &tmq, bar(C::BAR_QFULL + t), q0 + 128 * t, 0, b);
-          tma_load_3d(sQ + t * C::TILE_BYTES + C::BOX_BYTES, &tmq, bar(C::BAR_QFULL + t), q0 + 128 * t + 64, 0, b);
+          mbar_arrive_expect_tx(bar(C::BAR_QFULL + t), C::QTILE_BYTES);
+          tma_load_3d(sQ + t * C::QTILE_BYTES, &tmq, bar(C::BAR_QFULL + t), q0 + 128 * t, 0, b);
+          tma_load_3d(sQ + t * C::QTILE_BYTES + C::BOX_BYTES, &tmq, bar(C::BAR_QFULL + t), q0 + 128 * t + 64, 0, b);
         }
       }
       for (int j = 0; j < nj; ++j) {
-        const int s = j % C::KV_STAGES;
-        const uint32_t ph = (uint32_t)(j / C::KV_STAGES) & 1u;
-        const int tok = (prm.mode == MODE_CIRCULANT) ? (int)pmod(kbase + 128 * j, prm.N) : 128 * j;
-        mbar_wait(bar(C::BAR_KEMPTY + s), ph ^ 1u);
-        mbar_arrive_expect_tx(bar(C::BAR_KFULL + s), C::TILE_BYTES);
-        tma_load_3d(sK + s * C::TILE_BYTES, &tmk, bar(C::BAR_KFULL + s), tok, 0, b);
-        tma_load_3d(sK + s * C::TILE_BYTES + C::BOX_BYTES, &tmk, bar(C::BAR_KFULL + s), tok + 64, 0, b);
-        mbar_wait(bar(C::BAR_VEMPTY + s), ph ^ 1u);
-        mbar_arrive_expect_tx(bar(C::BAR_VFULL + s), C::TILE_BYTES);
-        tma_load_3d(sV + s * C::TILE_BYTES, &tmv, bar(C::BAR_VFULL + s), tok, 0, b);
-        tma_load_3d(sV + s * C::TILE_BYTES + C::BOX_BYTES, &tmv, bar(C::BAR_VFULL + s), tok + 64, 0, b);
+        const int sk = j % C::K_STAGES, sv = j % C::V_STAGES;
+        const int tok = (prm.mode == MODE_CIRCULANT) ? (int)pmod(kbase + BN * j, prm.N) : BN * j;
+        mbar_wait(bar(C::BAR_KEMPTY + sk), ((uint32_t)(j / C::K_STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar(C::BAR_KFULL + sk), C::BOX_BYTES);
+        tma_load_3d(sK + sk * C::BOX_BYTES, &tmk, bar(C::BAR_KFULL + sk), tok, 0, b);
+        mbar_wait(bar(C::BAR_VEMPTY + sv), ((uint32_t)(j / C::V_STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar(C::BAR_VFULL + sv), C::BOX_BYTES);
+        tma_load_3d(sV + sv * C::BOX_BYTES, &tmv, bar(C::BAR_VFULL + sv), tok, 0, b);
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);   // A, B MN-major
+    } else if (warp == 1 || warp == 3) {
+      // ------------------------------------------------------------ MMA issuer of Q tile t
+      // The whole warp runs this loop (all values warp-uniform -> uniform registers); only the
+      // tcgen05 instructions themselves are issued by one elected lane.
+      const int t = warp >> 1;
+      constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, BN);   // A, B MN-major
       // P takes the input format: mixing A = f16 with B = bf16 in one kind::f16 MMA raises
       // "illegal instruction" on sm_100a (measured, round 1), so bf16 inputs mean bf16 P.
-      constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);     // A in TMEM, B K-major
-      const uint32_t colS[2] = {tmem_base + C::COL_S0, tmem_base + C::COL_S1};
-      const uint32_t colO[2] = {tmem_base + C::COL_O0, tmem_base + C::COL_O1};
-      uint32_t pphase[2] = {0, 0};
-      for (int j = 0; j <= nj; ++j) {
-        bool k_waited = false, v_waited = false;
+      constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);    // A in TMEM, B K-major
+      const int jlo = tr[t].jlo, jhi = tr[t].jhi;
+      const uint64_t qdesc = make_smem_desc_sw128(sQ + t * C::QTILE_BYTES, C::BOX_BYTES, 1024);
+      const uint64_t kdesc = make_smem_desc_sw128(sK, C::BOX_BYTES, 1024);
+      const uint64_t vdesc = make_smem_desc_sw128(sV, 16, 1024);
+      const uint32_t tSt = tmem_base + C::COL_S + 128 * t;
+      const uint32_t tOt = tmem_base + C::COL_O + D * t;
+      for (int g = 0; g <= nj + 1; ++g) {
+        const int jp = g - 2;
+        // Both issuers wait for every K/V tile, used or not: the empty barriers count 2 arrivals
+        // per phase, so an issuer must never run a whole ring ahead of the producer.
+        if (jp >= 0 && jp < nj) mbar_wait(bar(C::BAR_VFULL + jp % C::V_STAGES), (uint32_t)(jp / C::V_STAGES) & 1u);
+        if (jp >= jlo && jp < jhi) {                                         // O_t += P_t(jp) V(jp)
+          const int sv = jp % C::V_STAGES, i = jp - jlo, bb = i & 1;
+          mbar_wait(bar(C::BAR_PFULL + 2 * t + bb), (uint32_t)(i >> 1) & 1u);
+          tc_fence_after();
+          const uint64_t vd = vdesc + (uint64_t)(sv * (C::BOX_BYTES >> 4));
+          const uint32_t tP = tSt + 64 * bb;
+          if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j >= 1 && tr[t].jlo <= j - 1 && j - 1 < tr[t].jhi) {        // O_t += P_t(j-1) V(j-1)
-            const int sv = (j - 1) % C::KV_STAGES;
-            if (!v_waited) { mbar_wait(bar(C::BAR_VFULL + sv), (uint32_t)((j - 1) / C::KV_STAGES) & 1u); v_waited = true; }
-            mbar_wait(bar(C::BAR_PFULL + t), pphase[t]); pphase[t] ^= 1u;
-            tc_fence_after();
-            const uint32_t vb = sV + sv * C::TILE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t bd = make_smem_desc_sw128(vb + (ks >> 2) * C::BOX_BYTES + (ks & 3) * 32, 16, 1024);
-              mma_ts(colO[t], colS[t] + ks * 8, bd, idesc_pv, (j - 1 > tr[t].jlo || ks > 0) ? 1u : 0u);
-            }
+            for (int ks = 0; ks < BN / 16; ++ks)
+              mma_ts(tOt, tP + ks * 8, vd + (uint64_t)(ks * 2), idesc_pv, (i > 0 || ks > 0) ? 1u : 0u);
+            tc_commit(bar(C::BAR_ODONE + t));
           }
-          if (j < nj && tr[t].jlo <= j && j < tr[t].jhi) {                // S_t = Q_t K(j)^T
-            const int sk = j % C::KV_STAGES;
-            if (j == tr[t].jlo) mbar_wait(bar(C::BAR_QFULL + t), 0);
-            if (!k_waited) { mbar_wait(bar(C::BAR_KFULL + sk), (uint32_t)(j / C::KV_STAGES) & 1u); k_waited = true; }
-            tc_fence_after();
-            const uint32_t qb = sQ + t * C::TILE_BYTES, kb = sK + sk * C::TILE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < D / 16; ++ks) {
-              const uint64_t ad = make_smem_desc_sw128(qb + ks * 2048, C::BOX_BYTES, 1024);
-              const uint64_t bd = make_smem_desc_sw128(kb + ks * 2048, C::BOX_BYTES, 1024);
-              mma_ss(colS[t], ad, bd, idesc_qk, ks > 0 ? 1u : 0u);
-            }
-            tc_commit(bar(C::BAR_SFULL + t));
-          }
+          __syncwarp();
         }
-        if (j >= 1) tc_commit(bar(C::BAR_VEMPTY + (j - 1) % C::KV_STAGES));
-        if (j < nj) tc_commit(bar(C::BAR_KEMPTY + j % C::KV_STAGES));
+        if (g < nj) mbar_wait(bar(C::BAR_KFULL + g % C::K_STAGES), (uint32_t)(g / C::K_STAGES) & 1u);
+        if (g >= jlo && g < jhi) {                                           // S_t[b] = Q_t K(g)^T
+          const int sk = g % C::K_STAGES, i = g - jlo, bb = i & 1;
+          if (i == 0) mbar_wait(bar(C::BAR_QFULL + t), 0);
+          tc_fence_after();
+          const uint64_t kd = kdesc + (uint64_t)(sk * (C::BOX_BYTES >> 4));
+          const uint32_t tS = tSt + 64 * bb;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks)
+              mma_ss(tS, qdesc + (uint64_t)(ks * 128), kd + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
+            tc_commit(bar(C::BAR_SFULL + 2 * t + bb));
+          }
+          __syncwarp();
+        }
+        // release the K/V slots of this step (every issuer arrives, whether or not it used them)
+        if (elect_one()) {
+          if (jp >= 0 && jp < nj) tc_commit(bar(C::BAR_VEMPTY + jp % C::V_STAGES));
+          if (g < nj) tc_commit(bar(C::BAR_KEMPTY + g % C::K_STAGES));
+        }
+        __syncwarp();
       }
-      tc_commit(bar(C::BAR_OFINAL + 0));
-      tc_commit(bar(C::BAR_OFINAL + 1));
+      if (elect_one()) tc_commit(bar(C::BAR_OFINAL + t));
+      __syncwarp();
     }
   } else {
     // -------------------------------------------------------------- softmax warpgroups
-    setmaxnreg_inc<224>();
+    setmaxnreg_inc<216>();
     const int t = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + (t == 0 ? C::COL_S0 : C::COL_S1);
-    const uint32_t tO = tmem_base + lane_addr + (t == 0 ? C::COL_O0 : C::COL_O1);
+    const uint32_t tS0 = tmem_base + lane_addr + C::COL_S + 128 * t;
+    const uint32_t tO = tmem_base + lane_addr + C::COL_O + D * t;
     const int qi = q0 + 128 * t + row;                 // query token of this thread
     const float scale = prm.scale_log2;
+    const int jlo = tr[t].jlo, jhi = tr[t].jhi;
 
-    if (tr[t].jhi > tr[t].jlo) {
+    if (jhi > jlo) {
       float m_true = -INFINITY, m_used = -INFINITY, l_run = 0.f;
-      uint32_t sphase = 0;
-      for (int j = tr[t].jlo; j < tr[t].jhi; ++j) {
-        mbar_wait(bar(C::BAR_SFULL + t), sphase); sphase ^= 1u;
+      for (int j = jlo; j < jhi; ++j) {
+        const int i = j - jlo, bb = i & 1;
+        const uint32_t tS = tS0 + 64 * bb;
+        mbar_wait(bar(C::BAR_SFULL + 2 * t + bb), (uint32_t)(i >> 1) & 1u);
         tc_fence_after();
-        uint32_t s[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(tS + 32 * c, s[c]);
+        uint32_t s[2][32];
+        tmem_ld32(tS, s[0]);
+        tmem_ld32(tS + 32, s[1]);
         tmem_wait_ld();
 
         // ---- mask (last dense tile / circulant band edges); lo <= col < hi stays
-        int lo = 0, hi = 128;
-        if (prm.mode == MODE_CIRCULANT) { lo = (qi - prm.p) - (kbase + 128 * j); hi = lo + prm.W; }
-        else { hi = prm.N - 128 * j; }
-        if (lo > 0 || hi < 128) {
+        int lo = 0, hi = BN;
+        if (prm.mode == MODE_CIRCULANT) { lo = (qi - prm.p) - (kbase + BN * j); hi = lo + prm.W; }
+        else { hi = prm.N - BN * j; }
+        if (lo > 0 || hi < BN) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int col = 32 * c + i;
-              if (col < lo || col >= hi) s[c][i] = 0xff800000u;   // -inf
+            for (int e = 0; e < 32; ++e) {
+              const int col = 32 * c + e;
+              if (col < lo || col >= hi) s[c][e] = 0xff800000u;   // -inf
             }
         }
         // ---- running max (thread-local: one thread owns one row)
-        float mx = -INFINITY;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx = fmaxf(mx, fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
-        m_true = fmaxf(m_true, mx * scale);
+        for (int e = 0; e < 32; e += 2) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[0][e]), __uint_as_float(s[0][e + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[1][e]), __uint_as_float(s[1][e + 1])));
+        }
+        m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
         // ---- lazy rescale of O and l (warp-uniform decision; this warp owns its 32 TMEM lanes)
         const bool want = (m_true - m_used) > RESCALE_THRESHOLD;   // inf on first use
         if (__any_sync(0xffffffffu, want)) {
           const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_true);
-          if (j > tr[t].jlo) {                        // O_t holds PV results only after the first tile
+          if (i > 0) {
+            // O_t holds PV(jlo .. j-1); PV(j-1) was issued after our previous arrive and must have
+            // completed before O is touched.  o_done counts one completion per PV_t.
+            mbar_wait(bar(C::BAR_ODONE + t), (uint32_t)(i - 1) & 1u);
+            tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < D / 32; ++c) {
               uint32_t o[32];
               tmem_ld32(tO + 32 * c, o);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
               tmem_st32(tO + 32 * c, o);
             }
           }
@@ -279,24 +303,24 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           m_used = m_true;
         }
         const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;   // guard (-inf)-(-inf)
-        // ---- P = exp2(s*scale - m) -> 16-bit, written over the first 64 columns of S
+        // ---- P = exp2(s*scale - m) -> 16-bit, written over the first 32 columns of this S buffer
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[c][i]), scale, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), scale, neg_m));
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(s[c][e]), scale, neg_m));
+            const float p1 = ex2(fmaf(__uint_as_float(s[c][e + 1]), scale, neg_m));
             sum0 += p0; sum1 += p1;
-            pk[i >> 1] = pack2<FMT>(p0, p1);
+            pk[e >> 1] = pack2<FMT>(p0, p1);
           }
           tmem_st16(tS + 16 * c, pk);
         }
         l_run += sum0 + sum1;
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(bar(C::BAR_PFULL + t));
+        mbar_arrive(bar(C::BAR_PFULL + 2 * t + bb));
       }
 
       // ---- epilogue: O / l -> global (token-contiguous rows: a warp writes 32 consecutive tokens)
@@ -313,8 +337,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           tmem_wait_ld();
           if (in_range) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              ob[(size_t)(32 * c + i) * prm.N] = __float2bfloat16_rn(__uint_as_float(o[i]) * inv_l);
+            for (int e = 0; e < 32; ++e)
+              ob[(size_t)(32 * c + e) * prm.N] = __float2bfloat16_rn(__uint_as_float(o[e]) * inv_l);
           }
         }
       } else {
@@ -326,8 +350,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           tmem_wait_ld();
           if (in_range) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              ob[(size_t)(32 * c + i) * prm.N] = __float2half_rn(__uint_as_float(o[i]) * inv_l);
+            for (int e = 0; e < 32; ++e)
+              ob[(size_t)(32 * c + e) * prm.N] = __float2half_rn(__uint_as_float(o[e]) * inv_l);
           }
         }
       }
@@ -409,7 +433,7 @@ bool tc_fwd_supported(const Geo& g, int dtype) {
   if (g.d != g.dv || (g.d != 64 && g.d != 128)) return false;
   if (g.N % 8 != 0 || g.N < 8 || g.N > 0x3fffffff) return false;    // TMA: 16-byte global strides
   if (g.B > 65535) return false;                                     // gridDim.y
-  if (g.mode == MODE_CIRCULANT && (g.N % 128 != 0)) return false;    // tile-aligned wrap-around
+  if (g.mode == MODE_CIRCULANT && (g.N % 64 != 0)) return false;     // tile-aligned wrap-around
   return true;
 }
 
