@@ -45,6 +45,19 @@ constexpr int BN = 64;                      // keys per K/V tile (one TMA box)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // lazy rescale: P may grow to 2^8 before O is rescaled
+// Tuning knobs, measured on B200 at the C3 shape over 40 back-to-back steps (power-capped, ~1650 MHz;
+// profiles/r1b_ab_variants.txt): packed f32x2 math +2 %; the TMEM prefetch of S(j+1) -2 %; emulating
+// 25 % of the exponentials on the FMA pipe -5 % (more instructions -> more power -> lower clocks).
+#ifndef FA_PREFETCH
+#define FA_PREFETCH 0
+#endif
+#ifndef FA_PACKED
+#define FA_PACKED 1
+#endif
+#ifndef FA_EMU_PER_32
+#define FA_EMU_PER_32 0
+#endif
+constexpr int EMU_PER_32 = FA_EMU_PER_32;   // exponentials per 32 emulated on the FMA pipe (8 = 25 %)
 
 template <int D>
 struct Cfg {
@@ -248,36 +261,47 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     const int jlo = tr[t].jlo, jhi = tr[t].jhi;
 
     if (jhi > jlo) {
-      float m_true = -INFINITY, m_used = -INFINITY, l_run = 0.f;
-      for (int j = jlo; j < jhi; ++j) {
+      float m_true = -INFINITY, m_used = -INFINITY;
+      const bool circ = prm.mode == MODE_CIRCULANT;
+      const int NN = prm.N, WW = prm.W, pp = prm.p;
+      float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);      // packed row-sum accumulators
+      const float2 scale2 = make_float2(scale, scale);
+
+      // One 64-key step on the S row held in `sc`; S(j+1) is prefetched from TMEM into `sn`
+      // BEFORE the exp phase (QK runs two steps ahead, so it is normally ready), which hides
+      // the mbarrier + tcgen05.ld latency behind the MUFU-bound part of the step.
+      auto softmax_step = [&](const int j, uint32_t (&sc)[2][32], uint32_t (&sn)[2][32]) {
         const int i = j - jlo, bb = i & 1;
         const uint32_t tS = tS0 + 64 * bb;
-        mbar_wait(bar(C::BAR_SFULL + 2 * t + bb), (uint32_t)(i >> 1) & 1u);
-        tc_fence_after();
-        uint32_t s[2][32];
-        tmem_ld32(tS, s[0]);
-        tmem_ld32(tS + 32, s[1]);
-        tmem_wait_ld();
-
+        // opportunistic prefetch of S(j+1): taken now only if the tensor pipe already delivered it
+        const bool more = j + 1 < jhi;
+        const uint32_t nbar = bar(C::BAR_SFULL + 2 * t + (bb ^ 1)), npar = (uint32_t)((i + 1) >> 1) & 1u;
+        bool fetched = false;
+        if (FA_PREFETCH && more && mbar_test_wait(nbar, npar)) {
+          tc_fence_after();
+          tmem_ld32(tS0 + 64 * (bb ^ 1), sn[0]);
+          tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);
+          fetched = true;
+        }
         // ---- mask (last dense tile / circulant band edges); lo <= col < hi stays
         int lo = 0, hi = BN;
-        if (prm.mode == MODE_CIRCULANT) { lo = (qi - prm.p) - (kbase + BN * j); hi = lo + prm.W; }
-        else { hi = prm.N - BN * j; }
+        if (circ) { lo = (qi - pp) - (kbase + BN * j); hi = lo + WW; }
+        else { hi = NN - BN * j; }
         if (lo > 0 || hi < BN) {
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               const int col = 32 * c + e;
-              if (col < lo || col >= hi) s[c][e] = 0xff800000u;   // -inf
+              if (col < lo || col >= hi) sc[c][e] = 0xff800000u;   // -inf
             }
         }
         // ---- running max (thread-local: one thread owns one row)
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s[0][e]), __uint_as_float(s[0][e + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s[1][e]), __uint_as_float(s[1][e + 1])));
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[0][e]), __uint_as_float(sc[0][e + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[1][e]), __uint_as_float(sc[1][e + 1])));
         }
         m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
         // ---- lazy rescale of O and l (warp-uniform decision; this warp owns its 32 TMEM lanes)
@@ -286,7 +310,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_true);
           if (i > 0) {
             // O_t holds PV(jlo .. j-1); PV(j-1) was issued after our previous arrive and must have
-            // completed before O is touched.  o_done counts one completion per PV_t.
+            // completed before O is touched.  o_done counts one completion per PV_t; at this point
+            // it is at most one phase behind (s_full(j) already implies PV(j-2) completed).
             mbar_wait(bar(C::BAR_ODONE + t), (uint32_t)(i - 1) & 1u);
             tc_fence_after();
 #pragma unroll 1
@@ -299,29 +324,71 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
               tmem_st32(tO + 32 * c, o);
             }
           }
-          l_run *= alpha;
+          l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
           m_used = m_true;
         }
         const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;   // guard (-inf)-(-inf)
-        // ---- P = exp2(s*scale - m) -> 16-bit, written over the first 32 columns of this S buffer
-        float sum0 = 0.f, sum1 = 0.f;
+        const float2 negm2 = make_float2(neg_m, neg_m);
+        // ---- P = exp2(s*scale - m) -> 16-bit, written over the first 32 columns of this S buffer.
+        // The last EMU elements of every 32 go through the FMA pipe (Cody-Waite split + degree-3
+        // minimax polynomial, rel. error 9e-5 << 16-bit P rounding) to unload the MUFU.
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(s[c][e]), scale, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(s[c][e + 1]), scale, neg_m));
-            sum0 += p0; sum1 += p1;
-            pk[e >> 1] = pack2<FMT>(p0, p1);
+#if FA_PACKED
+            float2 x = __ffma2_rn(make_float2(__uint_as_float(sc[c][e]), __uint_as_float(sc[c][e + 1])), scale2, negm2);
+#else
+            float2 x = make_float2(fmaf(__uint_as_float(sc[c][e]), scale, neg_m), fmaf(__uint_as_float(sc[c][e + 1]), scale, neg_m));
+#endif
+            float2 p;
+            if (e >= 32 - EMU_PER_32) {
+              x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+              const float2 xf = __fadd2_rd(x, make_float2(12582912.f, 12582912.f));    // floor(x) in the low mantissa bits
+              const float2 xr = __fadd2_rn(xf, make_float2(-12582912.f, -12582912.f)); // floor(x)
+              const float2 fr = __fadd2_rn(x, make_float2(-xr.x, -xr.y));              // frac in [0,1)
+              float2 q = __ffma2_rn(fr, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                                    make_float2(0.227564394474029541f, 0.227564394474029541f));
+              q = __ffma2_rn(q, fr, make_float2(0.695146143436431885f, 0.695146143436431885f));
+              q = __ffma2_rn(q, fr, make_float2(1.f, 1.f));
+              p.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(xf.x) << 23));
+              p.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(xf.y) << 23));
+            } else {
+              p.x = ex2(x.x); p.y = ex2(x.y);
+            }
+#if FA_PACKED
+            if (e & 2) l2b = __fadd2_rn(l2b, p); else l2a = __fadd2_rn(l2a, p);
+#else
+            l2a.x += p.x; l2a.y += p.y;
+#endif
+            pk[e >> 1] = pack2<FMT>(p.x, p.y);
           }
           tmem_st16(tS + 16 * c, pk);
         }
-        l_run += sum0 + sum1;
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar(C::BAR_PFULL + 2 * t + bb));
+        if (more && !fetched) {                // late path: S(j+1) was not ready before the exp phase
+          mbar_wait(nbar, npar);
+          tc_fence_after();
+          tmem_ld32(tS0 + 64 * (bb ^ 1), sn[0]);
+          tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);
+        }
+        tmem_wait_ld();                        // S(j+1) registers are valid from here on
+      };
+
+      uint32_t sA[2][32], sB[2][32];
+      mbar_wait(bar(C::BAR_SFULL + 2 * t), 0);
+      tc_fence_after();
+      tmem_ld32(tS0, sA[0]);
+      tmem_ld32(tS0 + 32, sA[1]);
+      tmem_wait_ld();
+      for (int j = jlo; j < jhi; j += 2) {
+        softmax_step(j, sA, sB);
+        if (j + 1 < jhi) softmax_step(j + 1, sB, sA);
       }
+      const float l_run = (l2a.x + l2a.y) + (l2b.x + l2b.y);
 
       // ---- epilogue: O / l -> global (token-contiguous rows: a warp writes 32 consecutive tokens)
       mbar_wait(bar(C::BAR_OFINAL + t), 0);
