@@ -162,8 +162,12 @@ int fa_dense_fwd(const void* q, const void* k, const void* v, void* o, float* l,
 }
 
 size_t fa_workspace_bytes_dense_bwd(int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags) {
-  (void)d; (void)dv; (void)dtype; (void)flags;
-  return align256((size_t)N * B * sizeof(float));          // delta
+  if (N <= 0 || B <= 0 || d <= 0 || dv <= 0) return 0;
+  const size_t simt = align256((size_t)N * B * sizeof(float));          // delta
+  const Geo g = dense_geo(N, d, dv, B);
+  if ((flags & FA_FLAG_FORCE_SIMT) || !tc_bwd_supported(g, dtype)) return simt;
+  const size_t tc = tc_bwd_workspace_bytes(g, dtype, flags);            // nlse, ndelta (+ fp16 re-encodings)
+  return simt > tc ? simt : tc;
 }
 
 int fa_dense_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
@@ -177,6 +181,7 @@ int fa_dense_bwd(const void* q, const void* k, const void* v, const void* o, con
   if ((rc = need_device())) return rc;
   const Geo g = dense_geo(N, d, dv, B);
   BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
+  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(g, dtype)) { set_path("tc"); return tc_bwd(g, a, dtype, flags, workspace, static_cast<cudaStream_t>(stream)); }
   set_path("simt");
   return simt_bwd(g, a, dtype, static_cast<cudaStream_t>(stream));
 }
@@ -221,6 +226,7 @@ int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o,
   if (!workspace || workspace_bytes < fa_workspace_bytes_circulant_bwd(N, d, dv, B, W, dtype, flags)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
   if ((rc = need_device())) return rc;
   BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
+  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(g, dtype)) { set_path("tc"); return tc_bwd(g, a, dtype, flags, workspace, static_cast<cudaStream_t>(stream)); }
   set_path("simt");
   return simt_bwd(g, a, dtype, static_cast<cudaStream_t>(stream));
 }

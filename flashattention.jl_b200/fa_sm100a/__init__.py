@@ -29,7 +29,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 __all__ = [
-    "lib", "FaError", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
+    "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
     "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys",
@@ -41,6 +41,7 @@ _LIB_PATH = os.environ.get("FA_SM100A_LIB", os.path.join(os.path.dirname(_HERE),
 
 FA_F32, FA_F16, FA_BF16 = 0, 1, 2
 FA_FLAG_FORCE_SIMT = 1
+FA_FLAG_BF16_INTERNALS = 2
 _DTYPES = {torch.float32: FA_F32, torch.float16: FA_F16, torch.bfloat16: FA_BF16}
 
 

@@ -52,6 +52,10 @@ typedef enum fa_dtype {
 /* flags (bit set) */
 #define FA_FLAG_NONE 0
 #define FA_FLAG_FORCE_SIMT 1   /* never take the tensor-core path (debug / exact arithmetic) */
+#define FA_FLAG_BF16_INTERNALS 2 /* backward, bf16 inputs: keep P and dS in bf16 for the MMAs (as FlashAttention-2/3
+                                    do) instead of re-encoding the inputs as scaled fp16 first.  Skips one pass over
+                                    q,k,v,dO and 4*N*d*B*2 bytes of workspace; gradients then carry the 2^-9 rounding
+                                    of bf16 P/dS (max-abs error 2-3e-3 of max instead of < 2e-3). */
 
 /* ---- host helpers -------------------------------------------------------------------- */
 int fa_version(void);                       /* FA_VERSION_MAJOR*100 + FA_VERSION_MINOR     */

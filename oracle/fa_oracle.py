@@ -442,6 +442,28 @@ def circulant_backward(Q, K, V, dO, W: int):
     return _F(dQ), _F(dK), _F(dV)
 
 
+def circulant_backward_given(Q, K, V, O, dO, l, m, W: int):
+    """Band-restricted ``OneDFastBack`` (src_cpp/FlashAttention.cpp:238-246) on the
+    SAVED forward results: ``P = exp(tau q.k - m) / l`` and ``D = rowsum(dO o O)`` use the
+    ``(O, l, m)`` the caller passes, as the flash backward does, instead of recomputing them."""
+    Q, K, V, O, dO = _F(Q), _F(K), _F(V), _F(O), _F(dO)
+    N, d, B = Q.shape
+    tau = Q.dtype.type(1) / Q.dtype.type(math.sqrt(d))
+    keys = circulant_keys(N, W)                                   # (W, N)
+    S = np.einsum("ikb,wikb->wib", Q, K[keys]) * tau
+    P = np.exp(S - np.asarray(m).reshape(1, N, B)) / np.asarray(l).reshape(1, N, B)      # cpp:239-240
+    dP = np.einsum("icb,wicb->wib", dO, V[keys])                                          # cpp:242
+    Di = (dO * O).sum(axis=1)[None, :, :]                                                 # cpp:243
+    dS = P * (dP - Di)                                                                    # cpp:244
+    dQ = np.einsum("wib,wikb->ikb", dS, K[keys]) * tau
+    dK = np.zeros_like(K)
+    dV = np.zeros_like(V)
+    flat = keys.reshape(-1)
+    np.add.at(dK, flat, (dS[:, :, None, :] * Q[None, :, :, :]).reshape(-1, d, B) * tau)
+    np.add.at(dV, flat, (P[:, :, None, :] * dO[None, :, :, :]).reshape(-1, V.shape[1], B))
+    return _F(dQ), _F(dK), _F(dV)
+
+
 # --------------------------------------------------------------------------------------
 # softmax
 # --------------------------------------------------------------------------------------

@@ -130,6 +130,66 @@ def test_dense_bwd(shape, dv, dtype):
     assert rel_err(to_np(dvv), dv0, dtype) < tol
 
 
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("N,d,B", [(128, 64, 1), (256, 128, 2), (384, 64, 3), (1024, 128, 2), (200, 64, 1),
+                                   (1000, 128, 1), (72, 64, 2), (520, 128, 1), (2048, 64, 1)])
+def test_dense_bwd_tc(N, d, B, dtype):
+    """tcgen05 backward (key-owner dK/dV kernel + query-owner dQ kernel) against the float64 oracle
+    (OneDFastBack, src_cpp/FlashAttention.cpp:194-252); also checks the run is bitwise reproducible
+    (no atomics), unlike the reference's racing accumulation (src_cpp/FlashAttention.cpp:299-312)."""
+    q, k, v = _qkv((N, d, B), d, dtype)
+    g = randn_np((N, d, B), 3, dtype)
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.dense_fa(Q, K, V)
+    # the oracle gets exactly what the kernel gets: Q, K, V, dO and the SAVED (O, l, m)
+    dq0, dk0, dv0 = fo.dense_fa_backward_blocked(*(t.astype(np.float64) for t in (q, k, v)), to_np(y),
+                                                 g.astype(np.float64), to_np(l), to_np(m))
+    dq, dk, dvv = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(dq), dq0, dtype) < 2e-3
+    assert rel_err(to_np(dk), dk0, dtype) < 2e-3
+    assert rel_err(to_np(dvv), dv0, dtype) < 2e-3
+    dq2, dk2, dv2 = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dvv, dv2)
+
+
+def test_dense_bwd_tc_scale_invariance_and_bf16_internals():
+    """bf16 inputs are re-encoded as power-of-two-scaled fp16 for the MMAs: tiny upstream gradients
+    (1e-6) and large logits must not lose precision.  FA_FLAG_BF16_INTERNALS keeps P/dS in bf16
+    (documented 4e-3 bound: the 2^-9 rounding of bf16 P/dS is itself 1.95e-3 per element)."""
+    N, d, B = 512, 128, 2
+    q, k, v = _qkv((N, d, B), d, BF16)
+    g = randn_np((N, d, B), 3, BF16)
+    q = np.asfortranarray(torch.from_numpy(q * 2.5).to(BF16).float().numpy())
+    g = np.asfortranarray(torch.from_numpy(g * 1e-6).to(BF16).float().numpy())
+    v = np.asfortranarray(torch.from_numpy(v * 300.0).to(BF16).float().numpy())
+    Q, K, V, G = (to_dev(t, BF16) for t in (q, k, v, g))
+    y, l, m = fa.dense_fa(Q, K, V)
+    want = fo.dense_fa_backward_blocked(*(t.astype(np.float64) for t in (q, k, v)), to_np(y), g.astype(np.float64),
+                                        to_np(l), to_np(m))
+    got = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    assert fa.last_path() == "tc"
+    for x, x0 in zip(got, want):
+        assert rel_err(to_np(x), x0, BF16) < 2e-3
+    fast = fa.dense_fa_backward(Q, K, V, y, G, l, m, flags=fa.FA_FLAG_BF16_INTERNALS)
+    for x, x0 in zip(fast, want):
+        assert rel_err(to_np(x), x0, BF16) < 4e-3
+
+
+def test_dense_bwd_tc_matches_exact_simt_at_size():
+    """Larger geometry (N=4096, d=128): the tcgen05 backward against this library's exact-fp32 SIMT
+    backward on the same bf16 inputs (the SIMT path is itself pinned to the oracle above)."""
+    N, d, B = 4096, 128, 2
+    Q, K, V, G = (fa.jl_randn((N, d, B), s, BF16) for s in range(4))
+    y, l, m = fa.dense_fa(Q, K, V)
+    a = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    assert fa.last_path() == "tc"
+    b_ = fa.dense_fa_backward(Q, K, V, y, G, l, m, flags=fa.FA_FLAG_FORCE_SIMT)
+    assert fa.last_path() == "simt"
+    for x, x0 in zip(a, b_):
+        assert rel_err(to_np(x), to_np(x0), BF16, want_rounded=True) < 2e-3
+
+
 # ------------------------------------------------------------------------------- circulant
 @pytest.mark.parametrize("N,d,B,W", [(64, 8, 2, 9), (256, 32, 1, 129), (128, 16, 2, 16), (40, 4, 1, 40),
                                      (700, 64, 1, 65), (1024, 64, 2, 255)])
@@ -164,6 +224,22 @@ def test_circulant_bwd(N, d, B, W, dtype):
     dq, dk, dvv = fa.circulant_fa_backward(q, k, v, O, g, l, m, W)
     tol = tol_for(dtype)
     assert rel_err(to_np(dq), dq0, dtype) < tol and rel_err(to_np(dk), dk0, dtype) < tol and rel_err(to_np(dvv), dv0, dtype) < tol
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("N,d,B,W", [(1024, 64, 2, 255), (512, 128, 1, 129), (512, 64, 2, 64), (256, 64, 1, 256),
+                                     (384, 64, 1, 5), (2048, 64, 1, 1023), (128, 128, 2, 33), (192, 64, 1, 192)])
+def test_circulant_bwd_tc(N, d, B, W, dtype):
+    Q, K, V, G = (randn_np((N, d, B), s, dtype) for s in range(4))
+    q, k, v, g = (to_dev(t, dtype) for t in (Q, K, V, G))
+    O, l, m = fa.circulant_fa(q, k, v, W)
+    dq0, dk0, dv0 = fo.circulant_backward_given(*(t.astype(np.float64) for t in (Q, K, V)), to_np(O),
+                                                G.astype(np.float64), to_np(l), to_np(m), W)
+    dq, dk, dvv = fa.circulant_fa_backward(q, k, v, O, g, l, m, W)
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(dq), dq0, dtype) < 2e-3
+    assert rel_err(to_np(dk), dk0, dtype) < 2e-3
+    assert rel_err(to_np(dvv), dv0, dtype) < 2e-3
 
 
 def test_circulant_rejects_bad_window():

@@ -283,3 +283,20 @@ def test_fused_softmax():
     assert np.allclose(fo.fused_softmax(S[:, :, 0], 2).sum(axis=1), 1)
     with pytest.raises(AssertionError):
         fo.fused_softmax(S, 3)
+
+
+def test_backward_given_forward_results_equals_recomputed():
+    """The flash backwards take the saved (O, l, m) (src_cpp/FlashAttention.cpp:194-252); with the
+    exact forward results they must reproduce the naive backwards that recompute everything."""
+    rng = np.random.default_rng(11)
+    Q, K, V, G = (np.asfortranarray(rng.standard_normal((48, 6, 2))) for _ in range(4))
+    O, l, m = fo.circulant_fa(Q, K, V, 9)
+    a = fo.circulant_backward_given(Q, K, V, O, G, l, m, 9)
+    b = fo.circulant_backward(Q, K, V, G, 9)
+    for x, y in zip(a, b):
+        assert np.abs(x - y).max() < 1e-12
+    O, l, m = fo.dense_fa(Q, K, V)
+    a = fo.dense_fa_backward_blocked(Q, K, V, O, G, l, m)
+    b = fo.dense_backward(Q, K, V, G)
+    for x, y in zip(a, b):
+        assert np.abs(x - y).max() < 1e-12

@@ -33,7 +33,7 @@ def to_np(t):
 STORAGE_HALF_ULP = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}
 
 
-def rel_err(got, want, storage=None):
+def rel_err(got, want, storage=None, want_rounded=False):
     """max|got-want| / max|want| over the finite entries; NaN patterns must coincide.
 
     With ``storage`` (a 16-bit torch dtype the result was STORED in), the unavoidable rounding of
@@ -49,7 +49,8 @@ def rel_err(got, want, storage=None):
     scale = np.abs(want[~nw]).max()
     diff = np.abs(got[~nw] - want[~nw])
     if storage in STORAGE_HALF_ULP:
-        diff = np.maximum(diff - STORAGE_HALF_ULP[storage] * np.abs(want[~nw]), 0.0)
+        # want_rounded: `want` is itself a result stored in the same 16-bit type (two roundings)
+        diff = np.maximum(diff - (2.0 if want_rounded else 1.0) * STORAGE_HALF_ULP[storage] * np.abs(want[~nw]), 0.0)
     return float(diff.max() / (scale if scale > 0 else 1.0))
 
 
