@@ -255,14 +255,15 @@ int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float*
   if ((rc = need_device())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FwdArgs a{q, k, v, y, nullptr, l, m};
-  set_path("simt");
+  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_win_supported(g, dtype);
+  set_path(tc ? "tc" : "simt");
   if (g.overlap) {
     a.acc = static_cast<float*>(workspace);
     FA_CUDA_TRY(cudaMemsetAsync(a.acc, 0, (size_t)g.N * dv * B * sizeof(float), st));
-    if ((rc = simt_fwd(g, a, dtype, st))) return rc;
+    if ((rc = tc ? tc_win_fwd(g, a, dtype, st) : simt_fwd(g, a, dtype, st))) return rc;
     return fold_finalize(g, a.acc, y, (int)dv, dtype, /*divide=*/1, st);     // src/windowed.jl:19
   }
-  if ((rc = simt_fwd(g, a, dtype, st))) return rc;
+  if ((rc = tc ? tc_win_fwd(g, a, dtype, st) : simt_fwd(g, a, dtype, st))) return rc;
   if (!full_cover(g)) return fill_uncovered_nan(g, y, (int)dv, dtype, st);   // 0/0 = NaN
   return FA_OK;
 }
@@ -296,7 +297,8 @@ int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y
   BwdArgs a{q, k, v, nullptr, d_y, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, reinterpret_cast<float*>(ws)};
   ws += align256((size_t)g.WD * g.L * B * sizeof(float));
   const size_t esz = dtype_size(dtype);
-  set_path("simt");
+  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_win_bwd_supported(g, dtype);
+  set_path(tc ? "tc" : "simt");
   if (g.overlap) {
     const size_t nq = (size_t)g.N * d * B, nv = (size_t)g.N * dv * B;
     a.aq = reinterpret_cast<float*>(ws); ws += align256(nq * 4);
@@ -305,7 +307,7 @@ int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y
     FA_CUDA_TRY(cudaMemsetAsync(a.aq, 0, nq * 4, st));
     FA_CUDA_TRY(cudaMemsetAsync(a.ak, 0, nq * 4, st));
     FA_CUDA_TRY(cudaMemsetAsync(a.av, 0, nv * 4, st));
-    if ((rc = simt_bwd(g, a, dtype, st))) return rc;
+    if ((rc = tc ? tc_win_bwd(g, a, dtype, st) : simt_bwd(g, a, dtype, st))) return rc;
     if ((rc = fold_finalize(g, a.aq, dq, (int)d, dtype, 0, st))) return rc;   // adjoint of unfold: fold, no division
     if ((rc = fold_finalize(g, a.ak, dk, (int)d, dtype, 0, st))) return rc;
     return fold_finalize(g, a.av, dv_out, (int)dv, dtype, 0, st);
@@ -315,7 +317,7 @@ int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y
     FA_CUDA_TRY(cudaMemsetAsync(dk, 0, (size_t)g.N * d * B * esz, st));
     FA_CUDA_TRY(cudaMemsetAsync(dv_out, 0, (size_t)g.N * dv * B * esz, st));
   }
-  return simt_bwd(g, a, dtype, st);
+  return tc ? tc_win_bwd(g, a, dtype, st) : simt_bwd(g, a, dtype, st);
 }
 
 // ------------------------------------------------------------------------------ unfold / fold

@@ -143,4 +143,11 @@ bool tc_bwd_supported(const Geo& g, int dtype);
 size_t tc_bwd_workspace_bytes(const Geo& g, int dtype, int flags);
 int tc_bwd(const Geo& g, const BwdArgs& a, int dtype, int flags, void* workspace, cudaStream_t st);
 
+// tensor-core windowed attention (one 128-row tile = floor(128 / W^D) windows): 16-bit dtypes,
+// d == dv in {64,128}, W^D <= 128
+bool tc_win_supported(const Geo& g, int dtype);
+int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
+bool tc_win_bwd_supported(const Geo& g, int dtype);
+int tc_win_bwd(const Geo& g, const BwdArgs& a, int dtype, cudaStream_t st);
+
 }  // namespace fa

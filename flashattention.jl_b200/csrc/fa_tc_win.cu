@@ -1,0 +1,770 @@
+// fa_tc_win.cu -- tcgen05 windowed attention for sm_100a: windowed_fa / block_fa
+// (reference src/windowed.jl:1-23) with window / unwindow (src/utils.jl:36-54) fused in.
+//
+// The reference materialises three unfolds, a permutedims, a dense attention over (W^D, d, L*B),
+// a fold and a ones-unfold-fold for the divisor.  Here a window is (part of) one tensor-core tile:
+//   * G = floor(128 / W^D) consecutive windows are packed into one 128-row tile (C2: 2 x 49 slots,
+//     C5: 1 x 125 slots); row = (window, slot).  A CTA works on NT tiles at a time, i.e. NT*G
+//     consecutive (x-adjacent) windows.
+//   * gather (the fused `window`): the CTA builds a small table {entry -> (global element offset,
+//     tile row)} whose warp-lanes run along x ACROSS the windows of the CTA, so one warp load
+//     touches as few 128-byte lines as the geometry allows (a window alone uses 10-14 bytes of a
+//     line).  Zero padding is a real token with q = k = v = 0, exactly as NNlib.unfold produces
+//     (SURVEY A.3).  Elements go to shared memory in the canonical SWIZZLE_128B [channel][token]
+//     layout (the layout a TMA box has in the dense kernels), so S = Q K^T is one M=128, N=128
+//     UMMA chain with MN-major operands and O = P V takes P from TMEM and V as a K-major operand.
+//   * softmax is row-local (thread == row) with a block-diagonal mask (columns of the row's window).
+//   * epilogue (the fused `unwindow`/fold): O rows are staged in fp32 over the dead Q/K tiles and
+//     scattered with the same x-contiguous lane mapping: 16-bit stores when windows do not overlap
+//     (stride >= W), fp32 atomicAdd into the fold accumulator when they do (fold_finalize then
+//     divides by the count, src/windowed.jl:16-19).
+// HBM-bound by design: q/k/v are read once per covering window, y written once.
+#include <cuda.h>
+#include "fa_common.cuh"
+#include "fa_ptx.cuh"
+
+namespace fa {
+namespace {
+
+using namespace ptx;
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int MAXE = 1024;     // table entries per CTA iteration (32 warp-items)
+constexpr int CB = 32;         // channels per gather / scatter unit
+
+template <int FMT> struct El { using type = __half; };
+template <> struct El<1> { using type = __nv_bfloat16; };
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if (FMT == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ unsigned short ldg_nc_u16(const void* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+
+// lane packing of the gather / scatter table (computed on the host)
+struct WinMap {
+  int G;          // windows per 128-row tile
+  int nwc;        // windows per CTA iteration = NT * G
+  int TW;         // tokens of one run group = nwc * W (contiguous in x when stride == W)
+  int RG;         // run groups = W^D / W
+  int gpw;        // TW <= 32: run groups per warp-item
+  int wpg;        // TW  > 32: warp-items per run group
+  int nwi;        // warp-items per CTA iteration (<= 32)
+};
+
+struct WinParams {
+  const void *q, *k, *v;
+  void* y;          // non-overlapping windows: output
+  float* acc;       // overlapping windows: fp32 fold accumulator (zero-initialised)
+  float *l, *m;     // (W^D, 1, L, B)
+  Geo g;
+  WinMap mp;
+  long long ngroups, nwin;
+  float scale_log2;
+};
+
+template <int D, int NT> struct WCfg {
+  static constexpr int THREADS = 128 * NT;
+  static constexpr int BOX_BYTES = 64 * D * 2;
+  static constexpr int TILE_BYTES = 2 * BOX_BYTES;
+  static constexpr int OFF_TILES = 0;                        // [NT][q,k,v]
+  static constexpr int OFF_SRC = NT * 3 * TILE_BYTES;        // long long[MAXE]
+  static constexpr int OFF_ROW = OFF_SRC + MAXE * 8;         // int[MAXE]
+  static constexpr int OFF_BAR = OFF_ROW + MAXE * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+  static constexpr int COLS_PER_TILE = (D == 64) ? 128 : 256;
+  static constexpr int TMEM_COLS = COLS_PER_TILE * NT;
+  static constexpr int COL_O = (D == 64) ? 64 : 128;         // P (64 cols) aliases S; O beside / after it
+  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS < 227 * 1024 / SMEM_BYTES ? 512 / TMEM_COLS : 227 * 1024 / SMEM_BYTES;
+};
+
+// ---- table: entry e = warp-item * 32 + lane  ->  (source element offset | -1, (tile << 8) | row | -1)
+__device__ __forceinline__ void build_table(const Geo& g, const WinMap& mp, long long gw0, long long nwin, int D,
+                                            long long* src, int* rowinfo, int tid, int nthreads, int* rowtok = nullptr) {
+  const int W = g.W, WD = g.WD;
+  for (int e = tid; e < mp.nwi * 32; e += nthreads) {
+    const int witem = e >> 5, lane = e & 31;
+    int rg, t;
+    bool has;
+    if (mp.TW <= 32) { const int gs = lane / mp.TW; t = lane - gs * mp.TW; rg = witem * mp.gpw + gs; has = gs < mp.gpw && rg < mp.RG; }
+    else { rg = witem / mp.wpg; t = (witem - rg * mp.wpg) * 32 + lane; has = t < mp.TW; }
+    long long so = -1;
+    int ri = -1;
+    if (has) {
+      const int win = t / W, kx = t - win * W;
+      const int slot = rg * W + kx;
+      const int ti = win / mp.G;
+      ri = (ti << 8) | ((win - ti * mp.G) * WD + slot);
+      const long long gw = gw0 + win;
+      if (gw < nwin) {
+        const long long b = gw / g.L;
+        const long long tok = window_slot_token(g, gw - b * g.L, slot);
+        if (tok >= 0) so = b * D * g.N + tok;
+        if (rowtok) rowtok[(ri >> 8) * 128 + (ri & 255)] = (int)tok;
+      } else if (rowtok) rowtok[(ri >> 8) * 128 + (ri & 255)] = -1;
+    }
+    src[e] = so;
+    rowinfo[e] = ri;
+  }
+}
+
+template <int D, int NT, int FMT>
+__global__ void __launch_bounds__(WCfg<D, NT>::THREADS, WCfg<D, NT>::CTAS_PER_SM)
+tc_win_fwd_kernel(const WinParams prm) {
+  using C = WCfg<D, NT>;
+  using T = typename El<FMT>::type;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sptr);
+  long long* tsrc = reinterpret_cast<long long*>(sptr + C::OFF_SRC);
+  int* trow = reinterpret_cast<int*>(sptr + C::OFF_ROW);
+  const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NWARPS = C::THREADS / 32;
+  const Geo& g = prm.g;
+  const WinMap mp = prm.mp;
+  const long long N = g.N;
+  const int WD = g.WD;
+
+  if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  // rows no window maps to (>= G * W^D) stay zero for the whole kernel: K/V pad rows must be finite
+  for (int i = tid; i < NT * 3 * C::TILE_BYTES / 16; i += C::THREADS)
+    reinterpret_cast<uint4*>(sptr)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // softmax role: thread == row `row` of tile `ti`
+  const int ti = tid >> 7, row = tid & 127;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t tS = tmem_base + lane_addr + ti * C::COLS_PER_TILE, tO = tS + C::COL_O;
+  const int wi = row / WD, slot = row - wi * WD;
+  const int c_lo = wi * WD, c_hi = c_lo + WD;           // columns of this row's own window
+  const unsigned short* tens[3] = {static_cast<const unsigned short*>(prm.q), static_cast<const unsigned short*>(prm.k),
+                                   static_cast<const unsigned short*>(prm.v)};
+  constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);
+  constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);
+  const float2 scale2 = make_float2(prm.scale_log2, prm.scale_log2);
+
+  uint32_t it = 0;
+  for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x, ++it) {
+    const long long gw0 = grp * mp.nwc;
+    build_table(g, mp, gw0, prm.nwin, D, tsrc, trow, tid, C::THREADS);
+    __syncthreads();
+
+    // ---- gather (fused `window`): unit = (warp-item, tensor, 32-channel block)
+    {
+      const int units = mp.nwi * 3 * (D / CB);
+      for (int u = warp; u < units; u += NWARPS) {
+        const int witem = u % mp.nwi, rest = u / mp.nwi;
+        const int x = rest % 3, c0 = (rest / 3) * CB;
+        const int e = witem * 32 + lane;
+        const int ri = trow[e];
+        if (ri < 0) continue;
+        const long long so = tsrc[e];
+        const int t_i = ri >> 8, rr = ri & 255;
+        const uint32_t dst = sbase + (uint32_t)((t_i * 3 + x) * C::TILE_BYTES + (rr >> 6) * C::BOX_BYTES + (rr & 7) * 2 + c0 * 128);
+        const uint32_t chunk = (uint32_t)((rr & 63) >> 3);
+        unsigned short v[CB];
+        if (so >= 0) {
+          const unsigned short* p = tens[x] + so + (long long)c0 * N;
+#pragma unroll
+          for (int j = 0; j < CB; ++j) v[j] = ldg_nc_u16(p + (long long)j * N);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CB; ++j) v[j] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < CB; ++j) sts_u16(dst + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4), v[j]);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- S = Q K^T per tile (M = 128 rows, N = 128 columns, K = D channels)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint64_t qdesc = make_smem_desc_sw128(sbase + (t * 3 + 0) * C::TILE_BYTES, C::BOX_BYTES, 1024);
+          const uint64_t kdesc = make_smem_desc_sw128(sbase + (t * 3 + 1) * C::TILE_BYTES, C::BOX_BYTES, 1024);
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tmem_base + t * C::COLS_PER_TILE, qdesc + (uint64_t)(ks * 128), kdesc + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_s);
+      }
+      __syncwarp();
+    }
+    const long long gw = gw0 + (long long)ti * mp.G + wi;
+    const bool valid = wi < mp.G && gw < prm.nwin;
+    mbar_wait(bar_s, it & 1u);
+    tc_fence_after();
+
+    // ---- softmax over the columns of this row's window (block-diagonal mask)
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t s[32];
+      tmem_ld32(tS + 32 * ch, s);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int col = 32 * ch + e;
+        if (col >= c_lo && col < c_hi) mx = fmaxf(mx, __uint_as_float(s[e]));
+      }
+    }
+    const float m2 = valid ? mx * prm.scale_log2 : 0.f;
+    const float2 negm2 = make_float2(-m2, -m2);
+    float lsum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t s[32], pk[16];
+      tmem_ld32(tS + 32 * ch, s);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const int col = 32 * ch + e;
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, negm2);
+        const float p0 = (valid && col >= c_lo && col < c_hi) ? ex2(x.x) : 0.f;
+        const float p1 = (valid && col + 1 >= c_lo && col + 1 < c_hi) ? ex2(x.y) : 0.f;
+        lsum += p0 + p1;
+        pk[e >> 1] = pack16<FMT>(p0, p1);
+      }
+      tmem_st16(tS + 16 * ch, pk);     // P (16-bit) over the S columns already consumed
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- O = P V per tile (A = P from TMEM, B = V K-major, K = 128 keys)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const uint64_t vdesc = make_smem_desc_sw128(sbase + (t * 3 + 2) * C::TILE_BYTES, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_ts(tmem_base + t * C::COLS_PER_TILE + C::COL_O, tmem_base + t * C::COLS_PER_TILE + ks * 8,
+                   vdesc + (uint64_t)((ks >> 2) * (C::BOX_BYTES >> 4) + (ks & 3) * 2), idesc_pv, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_o);
+      }
+      __syncwarp();
+    }
+    if (valid) {      // l, m for every slot, padded ones included
+      prm.l[gw * WD + slot] = lsum;
+      prm.m[gw * WD + slot] = m2 * LN2;
+    }
+    const float inv_l = valid ? 1.f / lsum : 0.f;
+    mbar_wait(bar_o, it & 1u);
+    tc_fence_after();
+
+    // ---- O rows -> fp32 staging [channel][128 rows] over the dead Q and K tiles of this tile
+    const uint32_t stage = sbase + (uint32_t)(ti * 3 * C::TILE_BYTES) + (uint32_t)row * 4u;
+#pragma unroll 1
+    for (int ch = 0; ch < D / 32; ++ch) {
+      uint32_t o[32];
+      tmem_ld32(tO + 32 * ch, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) sts_f32(stage + (uint32_t)((32 * ch + e) * 512), __uint_as_float(o[e]) * inv_l);
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- scatter (fused `unwindow` / fold) with the gather's lane mapping
+    {
+      const int units = mp.nwi * (D / CB);
+      for (int u = warp; u < units; u += NWARPS) {
+        const int witem = u % mp.nwi, c0 = (u / mp.nwi) * CB;
+        const int e = witem * 32 + lane;
+        const int ri = trow[e];
+        const long long so = tsrc[e];
+        if (ri < 0 || so < 0) continue;
+        const int t_i = ri >> 8, rr = ri & 255;
+        const uint32_t sa = sbase + (uint32_t)(t_i * 3 * C::TILE_BYTES) + (uint32_t)(rr * 4 + c0 * 512);
+        float v[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) v[j] = lds_f32(sa + (uint32_t)(j * 512));
+        if (prm.acc) {
+          float* a = prm.acc + so + (long long)c0 * N;
+#pragma unroll
+          for (int j = 0; j < CB; ++j) atomicAdd(a + (long long)j * N, v[j]);
+        } else {
+          T* y = static_cast<T*>(prm.y) + so + (long long)c0 * N;
+#pragma unroll
+          for (int j = 0; j < CB; ++j) y[(long long)j * N] = from_f32<T>(v[j]);
+        }
+      }
+    }
+    __syncthreads();      // staging (= Q/K tiles), table and TMEM are free for the next iteration
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+
+// =====================================================================================================
+// Backward (the reference has none): dYw = window(dY ./ count), per-window flash backward
+// with P recomputed from the saved (l, m), dq = unwindow(dQw) etc.  One 128-row tile per CTA iteration:
+//   A  gather q, k, v, dY tiles (bf16 inputs: per-tile power-of-two scales + in-place fp16 re-encoding,
+//      so P and dS carry 11 significand bits in the MMAs -- see fa_tc_bwd.cu)
+//   B  S = Q K^T, dP = dY V^T                        (thread == query row)
+//      D_i = sum_j P_ij dP_ij,  dS = P o (dP - D) / count_i  -> TMEM;  dQ = tau dS K
+//   C  S^T = K Q^T, dP^T = V dY^T                    (thread == key row; per-column stats from smem)
+//      P^T / count, dS^T -> TMEM;  dV = P^T dY,  dK = tau dS^T Q
+//   D  dQ, dV, dK rows staged in fp32 and scattered (16-bit stores, or fp32 atomics when windows overlap)
+// TMEM per tile: T1 = S / S^T at 0, T2 = dP / dP^T at 128, dQ over T1, P^T over T1, dS(^T) over T2,
+// dV and dK accumulators in the dead halves (d = 64) or in columns 256..511 (d = 128).
+template <int D> struct WBCfg {
+  static constexpr int THREADS = 128;
+  static constexpr int BOX_BYTES = 64 * D * 2;
+  static constexpr int TILE_BYTES = 2 * BOX_BYTES;
+  static constexpr int OFF_TILES = 0;                        // q, k, v, dy
+  static constexpr int BMAXE = 512;
+  static constexpr int OFF_SRC = 4 * TILE_BYTES;             // long long[BMAXE]
+  static constexpr int OFF_ROW = OFF_SRC + BMAXE * 8;        // int[BMAXE]
+  static constexpr int OFF_TOK = OFF_ROW + BMAXE * 4;        // int[128] token of every tile row
+  static constexpr int OFF_STAT = OFF_TOK + 128 * 4;         // float nlse[128], a[128], b[128]
+  static constexpr int OFF_AMAX = OFF_STAT + 3 * 128 * 4;    // uint[4]
+  static constexpr int OFF_BAR = OFF_AMAX + 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
+  static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;
+  static constexpr int COL_T1 = 0, COL_T2 = 128, COL_DQ = 0;
+  static constexpr int COL_DV = (D == 64) ? 64 : 256, COL_DK = (D == 64) ? 192 : 384;
+  static constexpr int CTAS_PER_SM = (D == 64) ? 2 : 1;
+};
+
+struct WinBwdParams {
+  const void *q, *k, *v, *dy;
+  const float *l, *m;
+  void *dq, *dk, *dv;        // non-overlapping windows: outputs
+  float *aq, *ak, *av;       // overlapping windows: fp32 fold accumulators (zero-initialised)
+  Geo g;
+  WinMap mp;
+  long long ngroups, nwin;
+  float scale_log2, tau;
+};
+
+__device__ __forceinline__ float pow2_norm_scale(uint32_t amax_bits) {   // s = 2^k with amax * s in [4, 8)
+  const int e = (int)((amax_bits >> 7) & 0xff);      // bf16 biased exponent (bits are |x| of a bf16 value)
+  if (e == 0 || e == 255) return 1.f;
+  int k = 129 - e;                                   // amax in [2^(e-127), 2^(e-126))  ->  [4, 8)
+  k = k > 100 ? 100 : (k < -100 ? -100 : k);
+  return __uint_as_float((uint32_t)(k + 127) << 23);
+}
+
+template <int D, int INBF>
+__global__ void __launch_bounds__(128, WBCfg<D>::CTAS_PER_SM)
+tc_win_bwd_kernel(const WinBwdParams prm) {
+  using C = WBCfg<D>;
+  using T = typename El<INBF>::type;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sptr);
+  long long* tsrc = reinterpret_cast<long long*>(sptr + C::OFF_SRC);
+  int* trow = reinterpret_cast<int*>(sptr + C::OFF_ROW);
+  int* rowtok = reinterpret_cast<int*>(sptr + C::OFF_TOK);
+  float* snl = reinterpret_cast<float*>(sptr + C::OFF_STAT);
+  float* sa = snl + 128;
+  float* sb = snl + 256;
+  unsigned int* samax = reinterpret_cast<unsigned int*>(sptr + C::OFF_AMAX);
+  const uint32_t bar_a = sbase + C::OFF_BAR, bar_b = bar_a + 8, tmem_slot = bar_a + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Geo& g = prm.g;
+  const WinMap mp = prm.mp;
+  const long long N = g.N;
+  const int WD = g.WD;
+
+  if (tid == 0) { mbar_init(bar_a, 1); mbar_init(bar_b, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  for (int i = tid; i < 4 * C::TILE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sptr)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128; i += 128) rowtok[i] = -1;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int row = tid;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t tT1 = tmem_base + lane_addr + C::COL_T1, tT2 = tmem_base + lane_addr + C::COL_T2;
+  const int wi = row / WD, slot = row - wi * WD;
+  const int c_lo = wi * WD, c_hi = c_lo + WD;
+  const unsigned short* tens[4] = {static_cast<const unsigned short*>(prm.q), static_cast<const unsigned short*>(prm.k),
+                                   static_cast<const unsigned short*>(prm.v), static_cast<const unsigned short*>(prm.dy)};
+  // MMAs always run in fp16: bf16 inputs are re-encoded tile by tile
+  constexpr uint32_t idesc_t = make_idesc_f16(0, 0, 1, 1, 128, 128);      // A, B MN-major, N = 128
+  constexpr uint32_t idesc_acc = make_idesc_f16(0, 0, 0, 0, 128, D);      // A in TMEM, B K-major, N = D
+  const uint32_t sQ = sbase, sK = sbase + C::TILE_BYTES, sV = sbase + 2 * C::TILE_BYTES, sG = sbase + 3 * C::TILE_BYTES;
+  auto mn = [&](uint32_t a) { return make_smem_desc_sw128(a, C::BOX_BYTES, 1024); };
+  auto km = [&](uint32_t a) { return make_smem_desc_sw128(a, 16, 1024); };
+  auto issue_T = [&](uint32_t x1, uint32_t y1, uint32_t x2, uint32_t y2, uint32_t bar) {   // T1 = X1 Y1^T, T2 = X2 Y2^T
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks)
+          mma_ss(tmem_base + C::COL_T1, mn(x1) + (uint64_t)(ks * 128), mn(y1) + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks)
+          mma_ss(tmem_base + C::COL_T2, mn(x2) + (uint64_t)(ks * 128), mn(y2) + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+        tc_commit(bar);
+      }
+      __syncwarp();
+    }
+  };
+  auto issue_acc = [&](uint32_t col_acc, uint32_t col_a, uint32_t ytile) {   // acc = A(TMEM, 128 x 128) * Y (K-major)
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      mma_ts(tmem_base + col_acc, tmem_base + col_a + ks * 8,
+             km(ytile) + (uint64_t)((ks >> 2) * (C::BOX_BYTES >> 4) + (ks & 3) * 2), idesc_acc, ks > 0 ? 1u : 0u);
+  };
+
+  uint32_t pa = 0, pb = 0;
+  for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x) {
+    const long long gw0 = grp * mp.nwc;
+    if (tid < 4) samax[tid] = 0;
+    build_table(g, mp, gw0, prm.nwin, D, tsrc, trow, tid, 128, rowtok);
+    __syncthreads();
+
+    // ---- A: gather q, k, v, dy
+    {
+      const int units = mp.nwi * 4 * (D / CB);
+      for (int u = warp; u < units; u += 4) {
+        const int witem = u % mp.nwi, rest = u / mp.nwi;
+        const int x = rest & 3, c0 = (rest >> 2) * CB;
+        const int e = witem * 32 + lane;
+        const int ri = trow[e];
+        uint32_t mx = 0;
+        if (ri >= 0) {
+          const long long so = tsrc[e];
+          const int rr = ri & 255;
+          const uint32_t dst = sbase + (uint32_t)(x * C::TILE_BYTES + (rr >> 6) * C::BOX_BYTES + (rr & 7) * 2 + c0 * 128);
+          const uint32_t chunk = (uint32_t)((rr & 63) >> 3);
+          unsigned short v[CB];
+          if (so >= 0) {
+            const unsigned short* p = tens[x] + so + (long long)c0 * N;
+#pragma unroll
+            for (int j = 0; j < CB; ++j) v[j] = ldg_nc_u16(p + (long long)j * N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CB; ++j) v[j] = 0;
+          }
+#pragma unroll
+          for (int j = 0; j < CB; ++j) {
+            sts_u16(dst + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4), v[j]);
+            if (INBF) mx = max(mx, (uint32_t)(v[j] & 0x7fff));
+          }
+        }
+        if (INBF) {
+          mx = __reduce_max_sync(0xffffffffu, mx);
+          if (lane == 0 && mx) atomicMax(&samax[x], mx);
+        }
+      }
+    }
+    __syncthreads();
+    float sq = 1.f, sk = 1.f, sv = 1.f, sg = 1.f;
+    if (INBF) {
+      // per-tile power-of-two scales, then bf16 -> fp16 in place (exact for everything within 2^-17 of the max)
+      sq = pow2_norm_scale(samax[0]); sk = pow2_norm_scale(samax[1]); sv = pow2_norm_scale(samax[2]); sg = pow2_norm_scale(samax[3]);
+      constexpr int VPT = C::TILE_BYTES / 16;      // 16-byte vectors per tensor tile
+      for (int i = tid; i < 4 * VPT; i += 128) {
+        const int x = i / VPT;
+        const float sc = x == 0 ? sq : x == 1 ? sk : x == 2 ? sv : sg;
+        uint4 u = reinterpret_cast<uint4*>(sptr)[i];
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2 h = __floats2half2_rn(__uint_as_float(w[j] << 16) * sc, __uint_as_float(w[j] & 0xffff0000u) * sc);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        reinterpret_cast<uint4*>(sptr)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- B: S = Q K^T, dP = dY V^T;  thread == query row
+    issue_T(sQ, sK, sG, sV, bar_a);
+    const long long gw = gw0 + wi;
+    const bool valid = wi < mp.G && gw < prm.nwin;
+    float nl = -INFINITY, rc = 1.f;
+    if (valid) {
+      nl = -(prm.m[gw * WD + slot] + logf(prm.l[gw * WD + slot])) * LOG2E;
+      const int tok = rowtok[row];
+      if (g.overlap && tok >= 0) rc = 1.f / (float)window_count_at(g, tok);     // dYw = window(dY ./ count)
+    }
+    const float sl2 = prm.scale_log2 / (sq * sk);
+    const float2 scale2 = make_float2(sl2, sl2), nl2 = make_float2(nl, nl);
+    mbar_wait(bar_a, pa & 1u); ++pa;
+    tc_fence_after();
+    float Dsum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t s[32], dp[32];
+      tmem_ld32(tT1 + 32 * ch, s);
+      tmem_ld32(tT2 + 32 * ch, dp);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const int col = 32 * ch + e;
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, nl2);
+        const float p0 = (col >= c_lo && col < c_hi) ? ex2(x.x) : 0.f;
+        const float p1 = (col + 1 >= c_lo && col + 1 < c_hi) ? ex2(x.y) : 0.f;
+        Dsum = fmaf(p0, __uint_as_float(dp[e]), Dsum);
+        Dsum = fmaf(p1, __uint_as_float(dp[e + 1]), Dsum);
+      }
+    }
+    if (!valid) Dsum = 0.f;
+    snl[row] = nl; sa[row] = rc; sb[row] = -Dsum * rc;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t s[32], dp[32], pk[16];
+      tmem_ld32(tT1 + 32 * ch, s);
+      tmem_ld32(tT2 + 32 * ch, dp);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const int col = 32 * ch + e;
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, nl2);
+        const float p0 = (col >= c_lo && col < c_hi) ? ex2(x.x) : 0.f;
+        const float p1 = (col + 1 >= c_lo && col + 1 < c_hi) ? ex2(x.y) : 0.f;
+        pk[e >> 1] = pack16<0>(p0 * (__uint_as_float(dp[e]) - Dsum) * rc, p1 * (__uint_as_float(dp[e + 1]) - Dsum) * rc);
+      }
+      tmem_st16(tT2 + 16 * ch, pk);      // dS (fp16) over the dP columns already consumed
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {                     // dQ = dS K  (accumulator over the dead S columns)
+      tc_fence_after();
+      if (elect_one()) { issue_acc(C::COL_DQ, C::COL_T2, sK); tc_commit(bar_b); }
+      __syncwarp();
+    }
+    mbar_wait(bar_b, pb & 1u); ++pb;
+    tc_fence_after();
+    float dq[D];
+    {
+      const float mul = prm.tau / (sv * sg * sk);
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tmem_base + lane_addr + C::COL_DQ + 32 * ch, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) dq[32 * ch + e] = __uint_as_float(o[e]) * mul;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- C: S^T = K Q^T, dP^T = V dY^T;  thread == key row, per-column (query) stats from smem
+    issue_T(sK, sQ, sV, sG, bar_a);
+    mbar_wait(bar_a, pa & 1u); ++pa;
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t s[32], dp[32], pk[16], dk[16];
+      tmem_ld32(tT1 + 32 * ch, s);
+      tmem_ld32(tT2 + 32 * ch, dp);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const int col = 32 * ch + e;
+        const float2 nlc = *reinterpret_cast<const float2*>(snl + col);
+        const float2 ac = *reinterpret_cast<const float2*>(sa + col);
+        const float2 bc = *reinterpret_cast<const float2*>(sb + col);
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, nlc);
+        const float p0 = (col >= c_lo && col < c_hi) ? ex2(x.x) : 0.f;
+        const float p1 = (col + 1 >= c_lo && col + 1 < c_hi) ? ex2(x.y) : 0.f;
+        pk[e >> 1] = pack16<0>(p0 * ac.x, p1 * ac.y);                                        // P^T / count_i
+        dk[e >> 1] = pack16<0>(p0 * fmaf(__uint_as_float(dp[e]), ac.x, bc.x), p1 * fmaf(__uint_as_float(dp[e + 1]), ac.y, bc.y));
+      }
+      tmem_st16(tT1 + 16 * ch, pk);
+      tmem_st16(tT2 + 16 * ch, dk);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {                     // dV = P^T dY,  dK = dS^T Q
+      tc_fence_after();
+      if (elect_one()) { issue_acc(C::COL_DV, C::COL_T1, sG); issue_acc(C::COL_DK, C::COL_T2, sQ); tc_commit(bar_b); }
+      __syncwarp();
+    }
+    mbar_wait(bar_b, pb & 1u); ++pb;
+    tc_fence_after();
+
+    // ---- D: stage one gradient at a time in fp32 [channel][128 rows] over the dead q/k tiles, scatter
+#pragma unroll 1
+    for (int which = 0; which < 3; ++which) {
+      const uint32_t stage = sbase + (uint32_t)row * 4u;
+      if (which == 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) sts_f32(stage + (uint32_t)(c * 512), dq[c]);
+      } else {
+        const float mul = which == 1 ? 1.f / sg : prm.tau / (sv * sg * sq);
+        const uint32_t tacc = tmem_base + lane_addr + (which == 1 ? C::COL_DV : C::COL_DK);
+#pragma unroll 1
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tacc + 32 * ch, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sts_f32(stage + (uint32_t)((32 * ch + e) * 512), __uint_as_float(o[e]) * mul);
+        }
+      }
+      __syncthreads();
+      float* accp = which == 0 ? prm.aq : which == 1 ? prm.av : prm.ak;
+      T* outp = static_cast<T*>(which == 0 ? prm.dq : which == 1 ? prm.dv : prm.dk);
+      const int units = mp.nwi * (D / CB);
+      for (int u = warp; u < units; u += 4) {
+        const int witem = u % mp.nwi, c0 = (u / mp.nwi) * CB;
+        const int e = witem * 32 + lane;
+        const int ri = trow[e];
+        const long long so = tsrc[e];
+        if (ri < 0 || so < 0) continue;
+        const uint32_t sadr = sbase + (uint32_t)((ri & 255) * 4 + c0 * 512);
+        float v[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) v[j] = lds_f32(sadr + (uint32_t)(j * 512));
+        if (accp) {
+          float* a = accp + so + (long long)c0 * N;
+#pragma unroll
+          for (int j = 0; j < CB; ++j) atomicAdd(a + (long long)j * N, v[j]);
+        } else {
+          T* y = outp + so + (long long)c0 * N;
+#pragma unroll
+          for (int j = 0; j < CB; ++j) y[(long long)j * N] = from_f32<T>(v[j]);
+        }
+      }
+      __syncthreads();
+    }
+    // the staging left fp32 bytes in the q and k tiles: rows no window maps to must read as zero
+    // (their dS / P^T entries are exact zeros, and 0 x garbage could be NaN in the accumulating MMAs)
+    {
+      const int r0 = mp.G * WD, npad = (128 - r0) * D * 2;
+      for (int i = tid; i < npad; i += 128) {
+        const int x = i / ((128 - r0) * D), rem = i - x * (128 - r0) * D;
+        const int c = rem / (128 - r0), r = r0 + rem - c * (128 - r0);
+        sts_u16(sbase + (uint32_t)(x * C::TILE_BYTES + (r >> 6) * C::BOX_BYTES + c * 128 + ((((r & 63) >> 3) ^ (c & 7)) << 4) + (r & 7) * 2), 0);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+bool make_map(const Geo& g, int NT, WinMap& mp) {
+  mp.G = 128 / g.WD;
+  mp.nwc = NT * mp.G;
+  mp.TW = mp.nwc * g.W;
+  mp.RG = g.WD / g.W;
+  mp.gpw = 1; mp.wpg = 1;
+  if (mp.TW <= 32) { mp.gpw = 32 / mp.TW; mp.nwi = (mp.RG + mp.gpw - 1) / mp.gpw; }
+  else { mp.wpg = (mp.TW + 31) / 32; mp.nwi = mp.RG * mp.wpg; }
+  return mp.nwi * 32 <= MAXE;
+}
+
+template <int D, int NT, int FMT>
+int launch_win_fwd(const Geo& g, const FwdArgs& a, cudaStream_t st) {
+  using C = WCfg<D, NT>;
+  WinParams prm;
+  prm.q = a.q; prm.k = a.k; prm.v = a.v; prm.y = a.o; prm.acc = a.acc; prm.l = a.l; prm.m = a.m;
+  prm.g = g;
+  if (!make_map(g, NT, prm.mp)) { set_error("tc_win_fwd: window table too large"); return FA_ERR_UNSUPPORTED; }
+  prm.nwin = g.L * g.B;
+  prm.ngroups = (prm.nwin + prm.mp.nwc - 1) / prm.mp.nwc;
+  prm.scale_log2 = g.tau * LOG2E;
+  auto kern = tc_win_fwd_kernel<D, NT, FMT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * C::CTAS_PER_SM;
+  const unsigned grid = (unsigned)(prm.ngroups < cap ? prm.ngroups : cap);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(prm);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+template <int D, int INBF>
+int launch_win_bwd(const Geo& g, const BwdArgs& a, cudaStream_t st) {
+  using C = WBCfg<D>;
+  WinBwdParams prm;
+  prm.q = a.q; prm.k = a.k; prm.v = a.v; prm.dy = a.d_o; prm.l = a.l; prm.m = a.m;
+  prm.dq = a.dq; prm.dk = a.dk; prm.dv = a.dv; prm.aq = a.aq; prm.ak = a.ak; prm.av = a.av;
+  prm.g = g;
+  if (!make_map(g, 1, prm.mp) || prm.mp.nwi * 32 > C::BMAXE) { set_error("tc_win_bwd: window table too large"); return FA_ERR_UNSUPPORTED; }
+  prm.nwin = g.L * g.B;
+  prm.ngroups = (prm.nwin + prm.mp.nwc - 1) / prm.mp.nwc;
+  prm.scale_log2 = g.tau * LOG2E; prm.tau = g.tau;
+  auto kern = tc_win_bwd_kernel<D, INBF>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * C::CTAS_PER_SM;
+  const unsigned grid = (unsigned)(prm.ngroups < cap ? prm.ngroups : cap);
+  kern<<<grid, 128, C::SMEM_BYTES, st>>>(prm);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+}  // namespace
+
+bool tc_win_supported(const Geo& g, int dtype);
+bool tc_win_bwd_supported(const Geo& g, int dtype) {
+  if (!tc_win_supported(g, dtype)) return false;
+  WinMap mp;
+  return make_map(g, 1, mp) && mp.nwi * 32 <= 512;
+}
+
+int tc_win_bwd(const Geo& g, const BwdArgs& a, int dtype, cudaStream_t st) {
+  if (!tc_win_bwd_supported(g, dtype)) { set_error("tc_win_bwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
+  const int bf = dtype == FA_BF16 ? 1 : 0;
+  if (g.d == 128) return bf ? launch_win_bwd<128, 1>(g, a, st) : launch_win_bwd<128, 0>(g, a, st);
+  return bf ? launch_win_bwd<64, 1>(g, a, st) : launch_win_bwd<64, 0>(g, a, st);
+}
+
+bool tc_win_supported(const Geo& g, int dtype) {
+  if (dtype != FA_BF16 && dtype != FA_F16) return false;
+  if (g.mode != MODE_WINDOWED) return false;
+  if (g.d != g.dv || (g.d != 64 && g.d != 128)) return false;
+  if (g.WD > 128 || g.WD < 1) return false;
+  WinMap mp;
+  return make_map(g, 2, mp);
+}
+
+int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
+  if (!tc_win_supported(g, dtype)) { set_error("tc_win_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
+  const int fmt = dtype == FA_BF16 ? 1 : 0;
+  if (g.d == 128) return fmt ? launch_win_fwd<128, 1, 1>(g, a, st) : launch_win_fwd<128, 1, 0>(g, a, st);
+  return fmt ? launch_win_fwd<64, 2, 1>(g, a, st) : launch_win_fwd<64, 2, 0>(g, a, st);
+}
+
+}  // namespace fa

@@ -275,6 +275,52 @@ def test_windowed_fwd(spatial, W, kws, dtype):
     assert rel_err(to_np(l), l0) < max(tol, 1e-5) and rel_err(to_np(m), m0) < max(tol, 1e-5)
 
 
+WIN_TC_CASES = [
+    ((64,), 16, dict(stride=16, pad=0), 64),          # 8 windows per 128-row tile
+    ((64,), 16, dict(stride=4, pad=0), 64),           # overlapping: atomic fold + count
+    ((22,), 5, dict(stride=5, pad=0), 64),            # uncovered positions -> NaN
+    ((20, 12), 7, {}, 64),                            # C2 geometry in small: 2 windows of 49 slots per tile
+    ((16, 16), 3, dict(stride=1, pad=1), 64),         # sliding 3x3
+    ((6, 7, 8), 3, {}, 64),                           # 3-D, 27 slots
+    ((12, 11, 10), 5, dict(stride=5, pad=3), 64),     # C5 geometry in small: 125 slots, 1 window per tile
+    ((9, 10), 11, dict(stride=11, pad=5), 128),       # 121 slots, d = 128
+    ((130,), 128, dict(stride=64, pad=0), 64),        # window fills the tile exactly
+]
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("spatial,W,kws,d", WIN_TC_CASES)
+def test_windowed_fwd_tc(spatial, W, kws, d, dtype):
+    B = 3
+    q, k, v = _qkv(spatial + (d, B), d, dtype)
+    y0, l0, m0 = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), W, **kws)
+    y, l, m = fa.windowed_fa(*(to_dev(t, dtype) for t in (q, k, v)), W, **kws)
+    assert fa.last_path() == "tc"
+    assert tuple(l.shape) == l0.shape
+    assert rel_err(to_np(y), y0, dtype) < 2e-3      # includes the NaN pattern
+    assert rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("spatial,W,kws,d", WIN_TC_CASES)
+def test_windowed_bwd_tc(spatial, W, kws, d, dtype):
+    B = 2
+    q, k, v = _qkv(spatial + (d, B), d, dtype)
+    g = randn_np(spatial + (d, B), 3, dtype)
+    dq0, dk0, dv0 = fo.windowed_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W, **kws)
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.windowed_fa(Q, K, V, W, **kws)
+    dq, dk, dvv = fa.windowed_fa_backward(Q, K, V, G, l, m, W, **kws)
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(dq), dq0, dtype) < 2e-3
+    assert rel_err(to_np(dk), dk0, dtype) < 2e-3
+    assert rel_err(to_np(dvv), dv0, dtype) < 2e-3
+    if not (kws.get("stride", W) < W):          # no atomics when windows do not overlap: reproducible
+        dq2, dk2, dv2 = fa.windowed_fa_backward(Q, K, V, G, l, m, W, **kws)
+        assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dvv, dv2)
+
+
 def test_windowed_fwd_config2_shape():
     # BASELINE config 2: 64x64 image, 7x7 window, d=64, batch 8 (defaults: stride 7, pad 3)
     q, k, v = _qkv((64, 64, 64, 8), 64, F32)
