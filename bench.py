@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="batch*heads per GPU (default: the named config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the backward / circulant / windowed legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -193,6 +194,68 @@ def main():
     value = total_flops / (ms * 1e-3) / 1e12
     per_gpu = value / world
 
+    # ---- the other legs of the named config and of the sharded configs (not part of `value`):
+    #      dense backward at the same shape, circulant C4 and windowed C5 forward/backward per GPU
+    extra = None
+    if not args.no_extra:
+        def timeit(fn, reps):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b_.record()
+            barrier()
+            t = a.elapsed_time(b_) / reps
+            if world > 1:
+                tt = torch.tensor([t], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
+            return t
+        peaks_x = measured_peaks()
+        extra = {}
+        # dense backward, same tensors (dO = randn), deterministic two-kernel tcgen05 backward
+        Bb = min(Bn, 128)                                   # bounded workspace (fp16 re-encodings of q,k,v,dO)
+        dO = fa.jl_empty((N, D, Bb), bf, dev).normal_()
+        sl = lambda t: fa.jl_array(t.permute(2, 1, 0)[:Bb].permute(2, 1, 0))
+        qb, kb, vb, Ob, lb, mb = (sl(t) for t in (q, k, v, O, l, m))
+        gb = dO
+        tb = timeit(lambda: fa.dense_fa_backward(qb, kb, vb, Ob, gb, lb, mb), max(2, args.steps // 3))
+        fl = 10.0 * N * N * D * Bb
+        extra["dense_bwd"] = {"ms": tb, "tflops_per_gpu": fl / tb / 1e9, "frac_tensor_peak": fl / tb / 1e9 / peaks_x["bf16_tflops"],
+                              "batch": Bb, "path": fa.last_path(), "flops": "10*N^2*d*B (7 GEMMs executed: deterministic dQ pass recomputes S, dP)"}
+        del dO, qb, kb, vb, Ob, gb, lb, mb
+        torch.cuda.empty_cache()
+        # C4: circulant 1-D forward, N=16384, W=255, d=64, B=512 total sharded over the ranks
+        Bc = 512 // world
+        cq, ck, cv = (fa.jl_empty((16384, 64, Bc), bf, dev).normal_() for _ in range(3))
+        cO = fa.jl_empty((16384, 64, Bc), bf, dev); cl = fa.jl_empty((16384, 1, Bc), torch.float32, dev); cm = fa.jl_empty((16384, 1, Bc), torch.float32, dev)
+        tc_ = timeit(lambda: fa.circulant_fa_(cO, cl, cm, cq, ck, cv, 255), args.steps)
+        by = (4 * 16384 * 64 * 2 + 8 * 16384) * Bc
+        extra["C4_circulant_fwd"] = {"ms": tc_, "batch_per_gpu": Bc, "tflops_per_gpu": 4.0 * 16384 * 255 * 64 * Bc / tc_ / 1e9,
+                                     "alg_gbs_per_gpu": by / tc_ / 1e6, "frac_hbm_peak": by / tc_ / 1e6 / peaks_x["hbm_gbs"],
+                                     "tokens_per_s": Bc * 16384 * world / tc_ * 1e3, "path": fa.last_path()}
+        del cq, ck, cv, cO, cl, cm
+        torch.cuda.empty_cache()
+        # C5: windowed 3-D forward + backward, 64^3 volume, W=5 (stride 5, pad 3), d=64, B=64 total sharded
+        Bw = max(1, 64 // world)
+        wq, wk, wv, wg = (fa.jl_empty((64, 64, 64, 64, Bw), bf, dev).normal_() for _ in range(4))
+        wy, wl, wm = fa.windowed_fa(wq, wk, wv, 5, 5, 3)
+        tf_ = timeit(lambda: fa.windowed_fa(wq, wk, wv, 5, 5, 3), max(2, args.steps // 2))
+        pf = fa.last_path()
+        tw_ = timeit(lambda: fa.windowed_fa_backward(wq, wk, wv, wg, wl, wm, 5, 5, 3), max(2, args.steps // 2))
+        ntok = 64 ** 3
+        byf = (4 * ntok * 64 * 2) * Bw + 8 * 125 * 2744 * Bw
+        byb = (7 * ntok * 64 * 2) * Bw + 8 * 125 * 2744 * Bw
+        extra["C5_windowed3d"] = {"batch_per_gpu": Bw, "fwd_ms": tf_, "bwd_ms": tw_,
+                                  "fwd_alg_gbs_per_gpu": byf / tf_ / 1e6, "bwd_alg_gbs_per_gpu": byb / tw_ / 1e6,
+                                  "fwd_frac_hbm_peak": byf / tf_ / 1e6 / peaks_x["hbm_gbs"], "bwd_frac_hbm_peak": byb / tw_ / 1e6 / peaks_x["hbm_gbs"],
+                                  "tokens_per_s_fwd": Bw * ntok * world / tf_ * 1e3, "path": pf + "/" + fa.last_path()}
+        del wq, wk, wv, wg, wy, wl, wm
+        torch.cuda.empty_cache()
+
     # ---- end to end: host (pinned) buffers through the public API, H2D + kernel + D2H every step
     e2e = None
     if not args.no_e2e:
@@ -238,7 +301,7 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": Bn, "l2": "inputs (3 GiB) larger than L2; no flush needed",
                        "sharding": "batch*heads across ranks, no collective"},
             "tokens_per_s": Bn * N * world / (ms * 1e-3), "tokens_per_s_batch_only": 16 * N * world * (Bn / 512) / (ms * 1e-3),
-            "gpu_launches": args.steps, "clocks": clocks, "roofline": roof, "e2e": e2e,
+            "gpu_launches": args.steps, "clocks": clocks, "roofline": roof, "e2e": e2e, "extra": extra,
         }
         if not args.no_cpu:
             cv, ct, cores = cpu_reference_tflops(2, 1, 8)

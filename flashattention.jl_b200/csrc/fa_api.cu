@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 
 #include "fa_common.cuh"
@@ -356,14 +357,25 @@ int fa_softmax(void* out, const void* in, int64_t M, int64_t N, int64_t B, int d
 
 // ------------------------------------------------------------------------------ host buffers
 namespace {
+// Grow-only per-device arena for the host-buffer entry points: cudaMalloc / cudaFree of ~0.5 GB per
+// call cost far more than the copies themselves, so the staging memory is kept between calls
+// (fa_release_host_staging() frees it).  Calls on one device are serialised by the arena lock.
+struct Arena {
+  std::mutex mu;
+  void* p = nullptr;
+  size_t cap = 0;
+};
+Arena g_arena[16];
+
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t n) { FA_CUDA_TRY(cudaMalloc(&p, n ? n : 1)); return FA_OK; }
+  bool owned = false;
+  ~DevBuf() { if (p && owned) cudaFree(p); }
+  int alloc(size_t n) { owned = true; FA_CUDA_TRY(cudaMalloc(&p, n ? n : 1)); return FA_OK; }
 };
 
 // Batch-chunked pipeline: H2D of chunk i+1 overlaps the kernels of chunk i and the D2H of
-// chunk i-1 (three streams).  `run(b0, nb, dq, dk, dv, do, dl, dm, stream)` enqueues the kernels.
+// chunk i-1 (two streams).  `run(nb, dq, dk, dv, do, dl, dm, stream)` enqueues the kernels.
 template <typename Run>
 int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l, float* m,
                   size_t q_elems_per_b, size_t v_elems_per_b, size_t stat_per_b, int64_t B, int dtype,
@@ -371,20 +383,27 @@ int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l
   int rc = need_device();
   if (rc) return rc;
   FA_CUDA_TRY(cudaSetDevice(device));
+  if (device < 0 || device >= 16) { set_error("device index out of range"); return FA_ERR_INVALID; }
   const size_t esz = dtype_size(dtype);
   const size_t per_b = (2 * q_elems_per_b + 2 * v_elems_per_b) * esz + 2 * stat_per_b * 4;
   int64_t chunk = B;
   const size_t target = (size_t)256 << 20;                 // ~256 MiB of tensors in flight per chunk
   if (per_b * (size_t)B > 2 * target) { chunk = (int64_t)(target / per_b); if (chunk < 1) chunk = 1; }
   const int nbuf = chunk < B ? 2 : 1;
+  const size_t bq = align256(chunk * q_elems_per_b * esz), bv = align256(chunk * v_elems_per_b * esz), bs = align256(chunk * stat_per_b * 4);
+  const size_t per_set = 2 * bq + 2 * bv + 2 * bs;
+  Arena& ar = g_arena[device];
+  std::lock_guard<std::mutex> lock(ar.mu);
+  if (ar.cap < per_set * nbuf) {
+    if (ar.p) { cudaFree(ar.p); ar.p = nullptr; ar.cap = 0; }
+    FA_CUDA_TRY(cudaMalloc(&ar.p, per_set * nbuf));
+    ar.cap = per_set * nbuf;
+  }
   DevBuf dq[2], dk[2], dvv[2], dout[2], dl[2], dm[2];
   for (int i = 0; i < nbuf; ++i) {
-    if ((rc = dq[i].alloc(chunk * q_elems_per_b * esz))) return rc;
-    if ((rc = dk[i].alloc(chunk * q_elems_per_b * esz))) return rc;
-    if ((rc = dvv[i].alloc(chunk * v_elems_per_b * esz))) return rc;
-    if ((rc = dout[i].alloc(chunk * v_elems_per_b * esz))) return rc;
-    if ((rc = dl[i].alloc(chunk * stat_per_b * 4))) return rc;
-    if ((rc = dm[i].alloc(chunk * stat_per_b * 4))) return rc;
+    char* base = static_cast<char*>(ar.p) + i * per_set;
+    dq[i].p = base; dk[i].p = base + bq; dvv[i].p = base + 2 * bq; dout[i].p = base + 2 * bq + bv;
+    dl[i].p = base + 2 * bq + 2 * bv; dm[i].p = base + 2 * bq + 2 * bv + bs;
   }
   cudaStream_t s[2];
   cudaEvent_t done[2];
@@ -458,6 +477,18 @@ int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, f
         void* w = ws[turn++ % 2].p;
         return fa_windowed_fwd(dq, dk, dvp, dop, dl, dm, ndim, dims, d, dv, nb, W, stride, pad, dtype, flags, w, wsb, st);
       });
+}
+
+int fa_release_host_staging(void) {
+  for (int d = 0; d < 16; ++d) {
+    std::lock_guard<std::mutex> lock(g_arena[d].mu);
+    if (g_arena[d].p) {
+      cudaSetDevice(d);
+      cudaFree(g_arena[d].p);
+      g_arena[d].p = nullptr; g_arena[d].cap = 0;
+    }
+  }
+  return FA_OK;
 }
 
 // ------------------------------------------------------------------------------ diagnostics

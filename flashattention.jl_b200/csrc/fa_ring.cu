@@ -1,0 +1,215 @@
+// fa_ring.cu -- multi-GPU pieces of the hot path.
+//
+// Every (batch*head) slice and every window is independent, so the normal multi-GPU mode is a
+// contiguous split of the trailing batch dim with NO collective (fa_shard_batch).  The one real
+// exchange step is a SINGLE long sequence that is sharded over the ranks by tokens: ring attention.
+//   rank r holds tokens [r*Nl, (r+1)*Nl) of q, k, v.  For s = 0..G-1 it runs the dense forward of
+//   its queries against the K/V block it currently holds (block of rank (r-s) mod G), merges the
+//   partial (O, l, m) with the online-softmax update of the reference (src/dense.jl:82-91), and
+//   -- on a second stream, overlapped with that compute -- passes the block to rank r+1 and
+//   receives the next one from rank r-1 with ncclSend/ncclRecv over NVLink.
+// NCCL is not linked: the symbols are resolved at run time from the libnccl the caller's
+// communicator was created with (torch's bundled one), so the library still loads without NCCL.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "fa_common.cuh"
+
+namespace fa {
+namespace {
+
+struct NcclApi {
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+const NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy already in the process
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if (h) {
+      api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(h, "ncclSend"));
+      api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(h, "ncclRecv"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+      api.ok = api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+    }
+  }
+  return api;
+}
+
+#define FA_NCCL_TRY(expr)                                                                     \
+  do {                                                                                        \
+    ncclResult_t _r = (expr);                                                                 \
+    if (_r != ncclSuccess) {                                                                  \
+      set_error("NCCL error %d (%s) at %s", (int)_r, nc.GetErrorString ? nc.GetErrorString(_r) : "?", #expr); \
+      return FA_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+// (Oa, la, ma) <- merge((Oa, la, ma), (Ob, lb, mb)); Oa is fp32 and normalised after every merge
+// exactly like O in src/dense.jl:82-91.  `out` (optional) receives Oa in the caller's dtype.
+template <typename T>
+__global__ void merge_partials_kernel(float* __restrict__ oa, float* __restrict__ la, float* __restrict__ ma,
+                                      const T* __restrict__ ob, const float* __restrict__ lb, const float* __restrict__ mb,
+                                      T* __restrict__ out, long long N, int dv, int first) {
+  const long long b = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const long long si = b * N + i;
+    const float m1 = first ? -INFINITY : ma[si], l1 = first ? 0.f : la[si];
+    const float m2 = mb[si], l2 = lb[si];
+    const float mn = fmaxf(m1, m2);
+    const float w1 = (m1 == -INFINITY) ? 0.f : l1 * __expf(m1 - mn);
+    const float w2 = (m2 == -INFINITY) ? 0.f : l2 * __expf(m2 - mn);
+    const float ln = w1 + w2;
+    const float inv = ln > 0.f ? 1.f / ln : 0.f;
+    const float c1 = w1 * inv, c2 = w2 * inv;
+    float* po = oa + b * dv * N + i;
+    const T* pb = ob + b * dv * N + i;
+    T* pout = out ? out + b * dv * N + i : nullptr;
+    for (int c = 0; c < dv; ++c) {
+      const float prev = first ? 0.f : po[(long long)c * N];
+      const float val = prev * c1 + to_f32(pb[(long long)c * N]) * c2;
+      po[(long long)c * N] = val;
+      if (pout) pout[(long long)c * N] = from_f32<T>(val);
+    }
+    la[si] = ln;
+    ma[si] = mn;
+  }
+}
+
+template <typename T>
+int merge_t(float* oa, float* la, float* ma, const void* ob, const float* lb, const float* mb, void* out,
+            long long N, int dv, long long B, int first, cudaStream_t st) {
+  const dim3 grid((unsigned)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024), (unsigned)B);
+  merge_partials_kernel<T><<<grid, 256, 0, st>>>(oa, la, ma, static_cast<const T*>(ob), lb, mb, static_cast<T*>(out), N, dv, first);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+int merge_partials(float* oa, float* la, float* ma, const void* ob, const float* lb, const float* mb, void* out,
+                   long long N, int dv, long long B, int dtype, int first, cudaStream_t st) {
+  if (dtype == FA_F32) return merge_t<float>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
+  if (dtype == FA_F16) return merge_t<__half>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
+  return merge_t<__nv_bfloat16>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
+}
+
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+int fa_shard_batch(int64_t B, int nranks, int rank, int64_t* begin, int64_t* count) {
+  if (B < 0 || nranks <= 0 || rank < 0 || rank >= nranks || !begin || !count) { set_error("bad shard arguments"); return FA_ERR_INVALID; }
+  const int64_t base = B / nranks, rem = B % nranks;       // the first `rem` ranks take one extra element
+  *count = base + (rank < rem ? 1 : 0);
+  *begin = rank * base + (rank < rem ? rank : rem);
+  return FA_OK;
+}
+
+int fa_merge_partials(float* o_acc, float* l_acc, float* m_acc, const void* o_blk, const float* l_blk,
+                      const float* m_blk, void* out, int64_t N, int64_t dv, int64_t B, int dtype, int first, void* stream) {
+  if (!o_acc || !l_acc || !m_acc || !o_blk || !l_blk || !m_blk || N <= 0 || dv <= 0 || B <= 0 || B > 65535) { set_error("bad merge arguments"); return FA_ERR_INVALID; }
+  if (dtype != FA_F32 && dtype != FA_F16 && dtype != FA_BF16) { set_error("bad dtype"); return FA_ERR_INVALID; }
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); set_error("no CUDA device available (libfa_sm100a has no CPU fallback)"); return FA_ERR_CUDA; }
+  return merge_partials(o_acc, l_acc, m_acc, o_blk, l_blk, m_blk, out, N, (int)dv, B, dtype, first, static_cast<cudaStream_t>(stream));
+}
+
+size_t fa_workspace_bytes_ring_dense_fwd(int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype) {
+  if (Nl <= 0 || d <= 0 || dv <= 0 || B <= 0) return 0;
+  const size_t esz = dtype_size(dtype);
+  return 2 * a256((size_t)Nl * d * B * esz) + 2 * a256((size_t)Nl * dv * B * esz)      // K, V receive buffers (double-buffered)
+         + a256((size_t)Nl * dv * B * esz) + 2 * a256((size_t)Nl * B * 4)               // block partial O, l, m
+         + a256((size_t)Nl * dv * B * 4);                                               // fp32 O accumulator
+}
+
+int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                      int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype, int flags,
+                      void* nccl_comm, int rank, int nranks, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (Nl <= 0 || d <= 0 || dv <= 0 || B <= 0 || B > 65535 || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bad ring arguments"); return FA_ERR_INVALID; }
+  if (dtype != FA_F32 && dtype != FA_F16 && dtype != FA_BF16) { set_error("bad dtype"); return FA_ERR_INVALID; }
+  if (nranks > 1 && !nccl_comm) { set_error("ring attention over %d ranks needs an NCCL communicator", nranks); return FA_ERR_INVALID; }
+  if (!workspace || workspace_bytes < fa_workspace_bytes_ring_dense_fwd(Nl, d, dv, B, dtype)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); set_error("no CUDA device available (libfa_sm100a has no CPU fallback)"); return FA_ERR_CUDA; }
+  const NcclApi& nc = nccl_api();
+  if (nranks > 1 && !nc.ok) { set_error("libnccl.so.2 (ncclSend/ncclRecv) could not be resolved"); return FA_ERR_CUDA; }
+
+  const size_t esz = dtype_size(dtype);
+  const size_t kb = a256((size_t)Nl * d * B * esz), vb = a256((size_t)Nl * dv * B * esz), sb = a256((size_t)Nl * B * 4);
+  char* ws = static_cast<char*>(workspace);
+  void* kbuf[2] = {ws, ws + kb};
+  void* vbuf[2] = {ws + 2 * kb, ws + 2 * kb + vb};
+  void* oblk = ws + 2 * kb + 2 * vb;
+  float* lblk = reinterpret_cast<float*>(ws + 2 * kb + 3 * vb);
+  float* mblk = reinterpret_cast<float*>(ws + 2 * kb + 3 * vb + sb);
+  float* oacc = reinterpret_cast<float*>(ws + 2 * kb + 3 * vb + 2 * sb);
+
+  cudaStream_t cs = static_cast<cudaStream_t>(stream), xs = nullptr;
+  cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr}, ev_start = nullptr;
+  int rc = FA_OK;
+  if (nranks > 1) {
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_compute[i], cudaEventDisableTiming));
+      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_comm[i], cudaEventDisableTiming));
+    }
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventRecord(ev_start, cs));            // inputs are ready on the caller's stream
+    FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_start, 0));
+  }
+  const int next = (rank + 1) % nranks, prev = (rank + nranks - 1) % nranks;
+  const ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+  const void* cur_k = k;
+  const void* cur_v = v;
+  for (int s = 0; s < nranks && rc == FA_OK; ++s) {
+    const int bi = s & 1;
+    if (s + 1 < nranks) {
+      // exchange on the second stream: send the block we hold, receive the next one into buf[bi];
+      // buf[bi] was the compute input of step s-1, so wait for that compute first.
+      if (s >= 1) FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_compute[(s - 1) & 1], 0));
+      FA_NCCL_TRY(nc.GroupStart());
+      FA_NCCL_TRY(nc.Send(cur_k, (size_t)Nl * d * B * esz, ncclUint8, next, comm, xs));
+      FA_NCCL_TRY(nc.Send(cur_v, (size_t)Nl * dv * B * esz, ncclUint8, next, comm, xs));
+      FA_NCCL_TRY(nc.Recv(kbuf[bi], (size_t)Nl * d * B * esz, ncclUint8, prev, comm, xs));
+      FA_NCCL_TRY(nc.Recv(vbuf[bi], (size_t)Nl * dv * B * esz, ncclUint8, prev, comm, xs));
+      FA_NCCL_TRY(nc.GroupEnd());
+      FA_CUDA_TRY(cudaEventRecord(ev_comm[bi], xs));
+    }
+    // compute on the caller's stream: partial attention against the resident block, then merge
+    rc = fa_dense_fwd(q, cur_k, cur_v, oblk, lblk, mblk, Nl, d, dv, B, dtype, flags, cs);
+    if (rc == FA_OK)
+      rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, s == 0, cs);
+    if (rc == FA_OK && s + 1 < nranks) {
+      FA_CUDA_TRY(cudaEventRecord(ev_compute[bi], cs));
+      FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_comm[bi], 0));          // next block must have arrived
+      cur_k = kbuf[bi];
+      cur_v = vbuf[bi];
+    }
+  }
+  if (nranks > 1) {
+    // the exchange stream's work is ordered before the caller's stream (last ev_comm was waited on)
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_compute[i]); cudaEventDestroy(ev_comm[i]); }
+    cudaEventDestroy(ev_start);
+    cudaStreamDestroy(xs);       // deferred by the runtime until its work has drained
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -33,7 +33,7 @@ __all__ = [
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
     "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys",
-    "dense_dpa", "windowed_dpa", "block_dpa", "circulant_dpa",
+    "dense_dpa", "windowed_dpa", "block_dpa", "circulant_dpa", "shard_batch", "ring_dense_fa",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -81,6 +81,11 @@ def _load():
         "fa_dense_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, ci]),
         "fa_circulant_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, i64, ci, ci, ci]),
         "fa_windowed_fwd_host": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, ci]),
+        "fa_release_host_staging": (ci, []),
+        "fa_shard_batch": (ci, [i64, ci, ci, pi64, pi64]),
+        "fa_merge_partials": (ci, [vp] * 7 + [i64, i64, i64, ci, ci, vp]),
+        "fa_workspace_bytes_ring_dense_fwd": (sz, [i64, i64, i64, i64, ci]),
+        "fa_ring_dense_fwd": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, vp, ci, ci, vp, sz, vp]),
         "fa_debug_umma_probe": (ci, [ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -95,7 +100,8 @@ EXPORTED_SYMBOLS = (
     "fa_window_count fa_dense_fwd fa_workspace_bytes_dense_bwd fa_dense_bwd fa_circulant_fwd "
     "fa_workspace_bytes_circulant_bwd fa_circulant_bwd fa_workspace_bytes_windowed_fwd fa_windowed_fwd "
     "fa_workspace_bytes_windowed_bwd fa_windowed_bwd fa_window fa_unwindow fa_softmax fa_dense_fwd_host "
-    "fa_circulant_fwd_host fa_windowed_fwd_host").split()
+    "fa_circulant_fwd_host fa_windowed_fwd_host fa_release_host_staging fa_shard_batch fa_merge_partials "
+    "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd").split()
 
 
 def _check(rc: int, what: str):
@@ -255,6 +261,56 @@ def dense_fa_backward(Q, K, V, O, dO, l, m, flags: int = 0):
                                 _ptr(dQ), _ptr(dK), _ptr(dV), N, d, dv, B, _dt(Q), flags,
                                 _ptr(ws), ws.numel(), _stream(Q)), "fa_dense_bwd")
     return dQ, dK, dV
+
+
+# --------------------------------------------------------------------------------------------
+# multi-GPU
+# --------------------------------------------------------------------------------------------
+def shard_batch(B: int, world: int, rank: int) -> Tuple[int, int]:
+    """``(begin, count)`` of the contiguous batch*head range rank ``rank`` of ``world`` owns.  The
+    trailing dim is the slowest in memory (src/dense.jl:6-8), so a shard is a pointer range and the
+    path needs no collective."""
+    b, c = ctypes.c_int64(0), ctypes.c_int64(0)
+    _check(lib.fa_shard_batch(int(B), int(world), int(rank), ctypes.byref(b), ctypes.byref(c)), "fa_shard_batch")
+    return int(b.value), int(c.value)
+
+
+def _nccl_comm_ptr(group, device):
+    import torch.distributed as dist
+    pg = group if group is not None else dist.distributed_c10d._get_default_group()
+    backend = pg._get_backend(torch.device(device))
+    if not hasattr(backend, "_comm_ptr"):
+        raise FaError("ring_dense_fa needs an NCCL process group (ProcessGroupNCCL._comm_ptr)")
+    return int(backend._comm_ptr())
+
+
+def ring_dense_fa(q, k, v, group=None, flags: int = 0):
+    """Ring attention forward for one long sequence sharded by TOKENS over the ranks of ``group``:
+    every rank passes its ``(Nl, d, B)`` shard of q, k, v and gets its ``(Nl, dv, B)`` slice of
+    ``dense_fa`` over the full sequence, plus ``l, m``.  K/V blocks travel round the ring over NCCL
+    (``fa_ring_dense_fwd``).  Without an initialised process group it degenerates to ``dense_fa``."""
+    import torch.distributed as dist
+    _same(q, k, v)
+    q, k, v = (jl_array(t) for t in (q, k, v))
+    if q.ndim != 3 or not q.is_cuda:
+        raise FaError("ring_dense_fa: q, k, v must be CUDA tensors of shape (N_local, d, B)")
+    Nl, d, B = (int(s) for s in q.shape)
+    dv = int(v.shape[1])
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    comm = None
+    if world > 1:
+        dist.barrier(group)                                  # makes sure the NCCL communicator exists
+        comm = ctypes.c_void_p(_nccl_comm_ptr(group, q.device))
+    O = jl_empty((Nl, dv, B), q.dtype, q.device)
+    l = jl_empty((Nl, 1, B), torch.float32, q.device)
+    m = jl_empty((Nl, 1, B), torch.float32, q.device)
+    ws = _workspace(lib.fa_workspace_bytes_ring_dense_fwd(Nl, d, dv, B, _dt(q)), q.device)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_ring_dense_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(O), _ptr(l), _ptr(m), Nl, d, dv, B, _dt(q), flags,
+                                     comm, rank, world, _ptr(ws), ws.numel(), _stream(q)), "fa_ring_dense_fwd")
+        torch.cuda.current_stream(q.device).synchronize()    # the workspace dies with this frame
+    return O, l, m
 
 
 # --------------------------------------------------------------------------------------------

@@ -138,6 +138,33 @@ int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, f
                          int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
                          int64_t W, int64_t stride, int64_t pad, int dtype, int flags, int device);
 
+/* ---- multi-GPU ------------------------------------------------------------------
+ * The path shards over the trailing batch*head dim (contiguous in memory, src/dense.jl:6-8,45) with no
+ * collective: fa_shard_batch gives rank `rank` of `nranks` its [begin, begin+count) range. */
+int fa_shard_batch(int64_t B, int nranks, int rank, int64_t* begin, int64_t* count);
+/* Online-softmax merge of a block partial into fp32 accumulators, the update rule of
+ * src/dense.jl:82-91: (o_acc, l_acc, m_acc) <- merge with (o_blk [dtype], l_blk, m_blk); o_acc stays
+ * normalised.  first != 0 ignores the accumulators' previous content.  out (optional) receives o_acc
+ * in `dtype`.  All (N, dv|1, B) column-major. */
+int fa_merge_partials(float* o_acc, float* l_acc, float* m_acc, const void* o_blk, const float* l_blk,
+                      const float* m_blk, void* out, int64_t N, int64_t dv, int64_t B, int dtype, int first,
+                      void* stream);
+/* Ring attention forward for ONE long sequence sharded by tokens: rank r holds tokens
+ * [r*Nl, (r+1)*Nl) of q, k, v ((Nl, d|dv, B) each) and receives its (Nl, dv, B) slice of
+ * dense_fa(q, k, v) over the full N = nranks*Nl sequence, plus l, m.  nranks steps of
+ * [dense forward against the resident K/V block, merge] with the blocks passed round the ring by
+ * ncclSend/ncclRecv on a second stream (overlapped).  nccl_comm is the caller's ncclComm_t (e.g.
+ * torch's ProcessGroupNCCL communicator); nranks == 1 needs none. */
+size_t fa_workspace_bytes_ring_dense_fwd(int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype);
+int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                      int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype, int flags,
+                      void* nccl_comm, int rank, int nranks, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* The *_host entry points keep their device staging buffers between calls (grow-only, per device);
+ * this frees them.  Returns FA_OK. */
+int fa_release_host_staging(void);
+
 #ifdef __cplusplus
 }
 #endif

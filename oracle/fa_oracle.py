@@ -152,6 +152,32 @@ def dense_fa(q, k, v, M: int = 32_000, threads: int = 1):
     return y, l, m
 
 
+def merge_partials(Oa, la, ma, Ob, lb, mb):
+    """Online-softmax merge of two partial results over disjoint key sets: the update rule of
+    src/dense.jl:82-91 (m = max, l rescaled by exp(m_old - m), O kept normalised)."""
+    mn = np.maximum(ma, mb)
+    wa = np.where(np.isneginf(ma), 0.0, la * np.exp(ma - mn))
+    wb = np.where(np.isneginf(mb), 0.0, lb * np.exp(mb - mn))
+    ln = wa + wb
+    return (Oa * wa + Ob * wb) / ln, ln, mn
+
+
+def ring_dense_fa(q_shards, k_shards, v_shards):
+    """Ring schedule of SURVEY 8e on a list of per-rank token shards: at step s rank r holds the
+    K/V block of rank (r - s) mod G, runs dense_fa of its queries against it and merges.  Returns
+    per-rank (O, l, m); equal to dense_fa on the concatenated sequence."""
+    G = len(q_shards)
+    out = []
+    for r in range(G):
+        acc = None
+        for s in range(G):
+            src = (r - s) % G
+            part = dense_fa(q_shards[r], k_shards[src], v_shards[src])
+            acc = part if acc is None else merge_partials(*acc, *part)
+        out.append(acc)
+    return out
+
+
 def dense_backward(Q, K, V, dO):
     """Naive backward, the runnable statement ``OneDNaiveBack``
     (src_cpp/FlashAttention.cpp:161-175).  Returns ``(dQ, dK, dV)``."""
