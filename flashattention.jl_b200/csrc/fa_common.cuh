@@ -116,6 +116,8 @@ struct FwdArgs {
   void* o;          // dense/circulant: output; windowed non-overlap: y; windowed overlap: unused
   float* acc;       // windowed overlap: fp32 fold accumulator (N*dv*B), zero-initialised
   float *l, *m;
+  int o_f32;        // tcgen05 dense/circulant forward only: `o` is float32 whatever the input dtype
+                    // (block partials of the ring pass must not be rounded to 16 bits before merging)
 };
 struct BwdArgs {
   const void *q, *k, *v, *o, *d_o;

@@ -12,6 +12,7 @@
 // communicator was created with (torch's bundled one), so the library still loads without NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <string.h>
 
 #include "fa_common.cuh"
 
@@ -58,9 +59,9 @@ const NcclApi& nccl_api() {
 
 // (Oa, la, ma) <- merge((Oa, la, ma), (Ob, lb, mb)); Oa is fp32 and normalised after every merge
 // exactly like O in src/dense.jl:82-91.  `out` (optional) receives Oa in the caller's dtype.
-template <typename T>
+template <typename TB, typename T>
 __global__ void merge_partials_kernel(float* __restrict__ oa, float* __restrict__ la, float* __restrict__ ma,
-                                      const T* __restrict__ ob, const float* __restrict__ lb, const float* __restrict__ mb,
+                                      const TB* __restrict__ ob, const float* __restrict__ lb, const float* __restrict__ mb,
                                       T* __restrict__ out, long long N, int dv, int first) {
   const long long b = blockIdx.y;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
@@ -74,7 +75,7 @@ __global__ void merge_partials_kernel(float* __restrict__ oa, float* __restrict_
     const float inv = ln > 0.f ? 1.f / ln : 0.f;
     const float c1 = w1 * inv, c2 = w2 * inv;
     float* po = oa + b * dv * N + i;
-    const T* pb = ob + b * dv * N + i;
+    const TB* pb = ob + b * dv * N + i;
     T* pout = out ? out + b * dv * N + i : nullptr;
     for (int c = 0; c < dv; ++c) {
       const float prev = first ? 0.f : po[(long long)c * N];
@@ -87,11 +88,11 @@ __global__ void merge_partials_kernel(float* __restrict__ oa, float* __restrict_
   }
 }
 
-template <typename T>
+template <typename TB, typename T>
 int merge_t(float* oa, float* la, float* ma, const void* ob, const float* lb, const float* mb, void* out,
             long long N, int dv, long long B, int first, cudaStream_t st) {
   const dim3 grid((unsigned)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024), (unsigned)B);
-  merge_partials_kernel<T><<<grid, 256, 0, st>>>(oa, la, ma, static_cast<const T*>(ob), lb, mb, static_cast<T*>(out), N, dv, first);
+  merge_partials_kernel<TB, T><<<grid, 256, 0, st>>>(oa, la, ma, static_cast<const TB*>(ob), lb, mb, static_cast<T*>(out), N, dv, first);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
 }
@@ -100,11 +101,14 @@ size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
+// blk_f32: the block partial is float32 although `dtype` (the type of `out`) is 16-bit
 int merge_partials(float* oa, float* la, float* ma, const void* ob, const float* lb, const float* mb, void* out,
-                   long long N, int dv, long long B, int dtype, int first, cudaStream_t st) {
-  if (dtype == FA_F32) return merge_t<float>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
-  if (dtype == FA_F16) return merge_t<__half>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
-  return merge_t<__nv_bfloat16>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
+                   long long N, int dv, long long B, int dtype, int blk_f32, int first, cudaStream_t st) {
+  if (dtype == FA_F32) return merge_t<float, float>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
+  if (dtype == FA_F16) return blk_f32 ? merge_t<float, __half>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st)
+                                      : merge_t<__half, __half>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
+  return blk_f32 ? merge_t<float, __nv_bfloat16>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st)
+                 : merge_t<__nv_bfloat16, __nv_bfloat16>(oa, la, ma, ob, lb, mb, out, N, dv, B, first, st);
 }
 
 }  // namespace fa
@@ -127,14 +131,14 @@ int fa_merge_partials(float* o_acc, float* l_acc, float* m_acc, const void* o_bl
   if (dtype != FA_F32 && dtype != FA_F16 && dtype != FA_BF16) { set_error("bad dtype"); return FA_ERR_INVALID; }
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); set_error("no CUDA device available (libfa_sm100a has no CPU fallback)"); return FA_ERR_CUDA; }
-  return merge_partials(o_acc, l_acc, m_acc, o_blk, l_blk, m_blk, out, N, (int)dv, B, dtype, first, static_cast<cudaStream_t>(stream));
+  return merge_partials(o_acc, l_acc, m_acc, o_blk, l_blk, m_blk, out, N, (int)dv, B, dtype, 0, first, static_cast<cudaStream_t>(stream));
 }
 
 size_t fa_workspace_bytes_ring_dense_fwd(int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype) {
   if (Nl <= 0 || d <= 0 || dv <= 0 || B <= 0) return 0;
   const size_t esz = dtype_size(dtype);
   return 2 * a256((size_t)Nl * d * B * esz) + 2 * a256((size_t)Nl * dv * B * esz)      // K, V receive buffers (double-buffered)
-         + a256((size_t)Nl * dv * B * esz) + 2 * a256((size_t)Nl * B * 4)               // block partial O, l, m
+         + a256((size_t)Nl * dv * B * 4) + 2 * a256((size_t)Nl * B * 4)                 // block partial O (fp32), l, m
          + a256((size_t)Nl * dv * B * 4);                                               // fp32 O accumulator
 }
 
@@ -156,10 +160,17 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
   char* ws = static_cast<char*>(workspace);
   void* kbuf[2] = {ws, ws + kb};
   void* vbuf[2] = {ws + 2 * kb, ws + 2 * kb + vb};
+  const size_t ob4 = a256((size_t)Nl * dv * B * 4);
   void* oblk = ws + 2 * kb + 2 * vb;
-  float* lblk = reinterpret_cast<float*>(ws + 2 * kb + 3 * vb);
-  float* mblk = reinterpret_cast<float*>(ws + 2 * kb + 3 * vb + sb);
-  float* oacc = reinterpret_cast<float*>(ws + 2 * kb + 3 * vb + 2 * sb);
+  float* lblk = reinterpret_cast<float*>(ws + 2 * kb + 2 * vb + ob4);
+  float* mblk = reinterpret_cast<float*>(ws + 2 * kb + 2 * vb + ob4 + sb);
+  float* oacc = reinterpret_cast<float*>(ws + 2 * kb + 2 * vb + ob4 + 2 * sb);
+  // block partials stay float32 when the tcgen05 forward runs (16-bit rounding of every partial
+  // would add up over the ring); the exact-fp32 SIMT fallback writes them in `dtype`
+  Geo gd;
+  memset(&gd, 0, sizeof(gd));
+  gd.mode = MODE_DENSE; gd.d = (int)d; gd.dv = (int)dv; gd.N = Nl; gd.B = B; gd.tau = 1.0f / sqrtf((float)d);
+  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(gd, dtype);
 
   cudaStream_t cs = static_cast<cudaStream_t>(stream), xs = nullptr;
   cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr}, ev_start = nullptr;
@@ -193,9 +204,15 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
       FA_CUDA_TRY(cudaEventRecord(ev_comm[bi], xs));
     }
     // compute on the caller's stream: partial attention against the resident block, then merge
-    rc = fa_dense_fwd(q, cur_k, cur_v, oblk, lblk, mblk, Nl, d, dv, B, dtype, flags, cs);
+    if (tc) {
+      FwdArgs fa_args{q, cur_k, cur_v, oblk, nullptr, lblk, mblk, /*o_f32=*/1};
+      set_path("tc");
+      rc = tc_fwd(gd, fa_args, dtype, cs);
+    } else {
+      rc = fa_dense_fwd(q, cur_k, cur_v, oblk, lblk, mblk, Nl, d, dv, B, dtype, flags, cs);
+    }
     if (rc == FA_OK)
-      rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, s == 0, cs);
+      rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, tc ? 1 : 0, s == 0, cs);
     if (rc == FA_OK && s + 1 < nranks) {
       FA_CUDA_TRY(cudaEventRecord(ev_compute[bi], cs));
       FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_comm[bi], 0));          // next block must have arrived

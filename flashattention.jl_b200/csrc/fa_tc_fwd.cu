@@ -91,6 +91,7 @@ struct TcParams {
   float* m;
   int N, B, W, p, mode;
   float scale_log2;      // tau * log2(e)
+  int o_f32;             // store O as float32
 };
 
 __host__ __device__ inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -395,7 +396,19 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       tc_fence_after();
       const float inv_l = 1.f / l_run;
       const bool in_range = qi < prm.N;
-      if (FMT == 1) {
+      if (prm.o_f32) {
+        float* ob = static_cast<float*>(prm.o) + (size_t)b * D * prm.N + qi;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + 32 * c, o);
+          tmem_wait_ld();
+          if (in_range) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) ob[(size_t)(32 * c + e) * prm.N] = __uint_as_float(o[e]) * inv_l;
+          }
+        }
+      } else if (FMT == 1) {
         __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(prm.o) + (size_t)b * D * prm.N + qi;
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
@@ -480,6 +493,7 @@ int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.B = (int)g.B; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
   prm.scale_log2 = g.tau * LOG2E;
+  prm.o_f32 = a.o_f32;
   auto kern = tc_fwd_kernel<D, FMT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM_BYTES));
   const dim3 grid((unsigned)((g.N + 255) / 256), (unsigned)g.B);

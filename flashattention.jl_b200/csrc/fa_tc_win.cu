@@ -31,7 +31,7 @@ using namespace ptx;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int MAXE = 1024;     // table entries per CTA iteration (32 warp-items)
-constexpr int CB = 32;         // channels per gather / scatter unit
+constexpr int CB = 64;         // channels per gather / scatter unit (64 loads in flight per lane)
 
 template <int FMT> struct El { using type = __half; };
 template <> struct El<1> { using type = __nv_bfloat16; };
@@ -44,12 +44,39 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
 }
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ unsigned short ldg_nc_u16(const void* p) {
-  unsigned short v;
-  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+// 16-bit loads/stores through 32-bit registers (zero-extended / truncated): no PRMT repacking
+__device__ __forceinline__ uint32_t ldg_nc_u16(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void sts_u16(uint32_t a, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// one gather unit: NCH channels of one token (element offset `so`, -1 = zero padding) into the
+// SWIZZLE_128B [channel][token] tile; `dst` = smem address of (row, first channel) before swizzling
+template <int NCH>
+__device__ __forceinline__ uint32_t gather_unit(const unsigned short* base, long long so, long long N, uint32_t dst, uint32_t chunk) {
+  uint32_t sw[8];
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) sw[kk] = dst + ((chunk ^ (uint32_t)kk) << 4);
+  uint32_t v[NCH];
+  if (so >= 0) {
+    const char* p = reinterpret_cast<const char*>(base + so);
+    const long long sb = N * 2;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) v[j] = ldg_nc_u16(p + j * sb);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) v[j] = 0;
+  }
+  uint32_t mx = 0;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    sts_u16(sw[j & 7] + (uint32_t)(j * 128), v[j]);
+    mx = max(mx, v[j] & 0x7fffu);
+  }
+  return mx;     // max |x| bit pattern (used by the bf16 re-encoding of the backward)
+}
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 
@@ -82,7 +109,8 @@ template <int D, int NT> struct WCfg {
   static constexpr int OFF_TILES = 0;                        // [NT][q,k,v]
   static constexpr int OFF_SRC = NT * 3 * TILE_BYTES;        // long long[MAXE]
   static constexpr int OFF_ROW = OFF_SRC + MAXE * 8;         // int[MAXE]
-  static constexpr int OFF_BAR = OFF_ROW + MAXE * 4;
+  static constexpr int OFF_WIN = OFF_ROW + MAXE * 4;         // int4[256] window origins
+  static constexpr int OFF_BAR = OFF_WIN + 256 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
   static constexpr int COLS_PER_TILE = (D == 64) ? 128 : 256;
   static constexpr int TMEM_COLS = COLS_PER_TILE * NT;
@@ -91,7 +119,29 @@ template <int D, int NT> struct WCfg {
 };
 
 // ---- table: entry e = warp-item * 32 + lane  ->  (source element offset | -1, (tile << 8) | row | -1)
-__device__ __forceinline__ void build_table(const Geo& g, const WinMap& mp, long long gw0, long long nwin, int D,
+// wininfo[win] = {x0, y0, z0, batch | -1}: origin (first token per dim, may be negative = padding) of
+// every window of this CTA iteration, computed once per window; entries then need 32-bit math only.
+__device__ __forceinline__ void build_wininfo(const Geo& g, const WinMap& mp, long long gw0, long long nwin, int4* wininfo, int tid) {
+  if (tid < mp.nwc) {
+    const long long gw = gw0 + tid;
+    int4 wi4 = make_int4(0, 0, 0, -1);
+    if (gw < nwin) {
+      const long long b = gw / g.L;
+      int w = (int)(gw - b * g.L);
+      int o3[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int wk = w % g.o[k];
+        w /= g.o[k];
+        o3[k] = (k < g.nd) ? wk * g.stride - g.pad : 0;
+      }
+      wi4 = make_int4(o3[0], o3[1], o3[2], (int)b);
+    }
+    wininfo[tid] = wi4;
+  }
+}
+
+__device__ __forceinline__ void build_table(const Geo& g, const WinMap& mp, const int4* wininfo, int D,
                                             long long* src, int* rowinfo, int tid, int nthreads, int* rowtok = nullptr) {
   const int W = g.W, WD = g.WD;
   for (int e = tid; e < mp.nwi * 32; e += nthreads) {
@@ -104,16 +154,20 @@ __device__ __forceinline__ void build_table(const Geo& g, const WinMap& mp, long
     int ri = -1;
     if (has) {
       const int win = t / W, kx = t - win * W;
+      const int kz = rg / W, ky = rg - kz * W;             // rg = ky + W kz (0 beyond the spatial rank)
       const int slot = rg * W + kx;
       const int ti = win / mp.G;
       ri = (ti << 8) | ((win - ti * mp.G) * WD + slot);
-      const long long gw = gw0 + win;
-      if (gw < nwin) {
-        const long long b = gw / g.L;
-        const long long tok = window_slot_token(g, gw - b * g.L, slot);
-        if (tok >= 0) so = b * D * g.N + tok;
-        if (rowtok) rowtok[(ri >> 8) * 128 + (ri & 255)] = (int)tok;
-      } else if (rowtok) rowtok[(ri >> 8) * 128 + (ri & 255)] = -1;
+      const int4 wi4 = wininfo[win];
+      int tok = -1;
+      if (wi4.w >= 0) {
+        const int x = wi4.x + kx, y = wi4.y + ky, z = wi4.z + kz;
+        if (x >= 0 && x < g.s[0] && y >= 0 && y < g.s[1] && z >= 0 && z < g.s[2]) {
+          tok = (z * g.s[1] + y) * g.s[0] + x;
+          so = (long long)wi4.w * D * g.N + tok;
+        }
+      }
+      if (rowtok) rowtok[(ri >> 8) * 128 + (ri & 255)] = tok;
     }
     src[e] = so;
     rowinfo[e] = ri;
@@ -130,6 +184,7 @@ tc_win_fwd_kernel(const WinParams prm) {
   const uint32_t sbase = smem_u32(sptr);
   long long* tsrc = reinterpret_cast<long long*>(sptr + C::OFF_SRC);
   int* trow = reinterpret_cast<int*>(sptr + C::OFF_ROW);
+  int4* wininfo = reinterpret_cast<int4*>(sptr + C::OFF_WIN);
   const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = C::THREADS / 32;
@@ -164,7 +219,9 @@ tc_win_fwd_kernel(const WinParams prm) {
   uint32_t it = 0;
   for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x, ++it) {
     const long long gw0 = grp * mp.nwc;
-    build_table(g, mp, gw0, prm.nwin, D, tsrc, trow, tid, C::THREADS);
+    build_wininfo(g, mp, gw0, prm.nwin, wininfo, tid);
+    __syncthreads();
+    build_table(g, mp, wininfo, D, tsrc, trow, tid, C::THREADS);
     __syncthreads();
 
     // ---- gather (fused `window`): unit = (warp-item, tensor, 32-channel block)
@@ -179,18 +236,7 @@ tc_win_fwd_kernel(const WinParams prm) {
         const long long so = tsrc[e];
         const int t_i = ri >> 8, rr = ri & 255;
         const uint32_t dst = sbase + (uint32_t)((t_i * 3 + x) * C::TILE_BYTES + (rr >> 6) * C::BOX_BYTES + (rr & 7) * 2 + c0 * 128);
-        const uint32_t chunk = (uint32_t)((rr & 63) >> 3);
-        unsigned short v[CB];
-        if (so >= 0) {
-          const unsigned short* p = tens[x] + so + (long long)c0 * N;
-#pragma unroll
-          for (int j = 0; j < CB; ++j) v[j] = ldg_nc_u16(p + (long long)j * N);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CB; ++j) v[j] = 0;
-        }
-#pragma unroll
-        for (int j = 0; j < CB; ++j) sts_u16(dst + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4), v[j]);
+        gather_unit<CB>(tens[x] + (long long)c0 * N, so, N, dst, (uint32_t)((rr & 63) >> 3));
       }
     }
     fence_proxy_async();
@@ -217,38 +263,78 @@ tc_win_fwd_kernel(const WinParams prm) {
     mbar_wait(bar_s, it & 1u);
     tc_fence_after();
 
-    // ---- softmax over the columns of this row's window (block-diagonal mask)
+    // ---- softmax over the columns of this row's window (block-diagonal mask).  Each 32-column chunk
+    // is classified per warp: entirely inside every lane's window (no predicates), entirely outside
+    // (P = 0, S not even read), or mixed (per-element select).  Rows no window maps to take the
+    // "inside" path with m = +inf, i.e. P = exp2(-inf) = 0.
+    const int r_lo = valid ? c_lo : 0, r_hi = valid ? c_hi : 128;
+    uint32_t cls = 0;                                    // 2 bits per chunk: 1 = inside, 2 = outside, 0 = mixed
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const bool in = r_lo <= 32 * ch && 32 * ch + 32 <= r_hi, out = r_hi <= 32 * ch || r_lo >= 32 * ch + 32;
+      cls |= (__all_sync(0xffffffffu, in) ? 1u : (__all_sync(0xffffffffu, out) ? 2u : 0u)) << (2 * ch);
+    }
     float mx = -INFINITY;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
+      const uint32_t k = (cls >> (2 * ch)) & 3u;
+      if (k == 2u) continue;
       uint32_t s[32];
       tmem_ld32(tS + 32 * ch, s);
       tmem_wait_ld();
+      if (k == 1u) {
+        float m0 = mx, m1 = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int col = 32 * ch + e;
-        if (col >= c_lo && col < c_hi) mx = fmaxf(mx, __uint_as_float(s[e]));
+        for (int e = 0; e < 32; e += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(s[e]), __uint_as_float(s[e + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])));
+        }
+        mx = fmaxf(m0, m1);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = 32 * ch + e;
+          if (col >= r_lo && col < r_hi) mx = fmaxf(mx, __uint_as_float(s[e]));
+        }
       }
     }
-    const float m2 = valid ? mx * prm.scale_log2 : 0.f;
+    const float m2 = valid ? mx * prm.scale_log2 : INFINITY;
     const float2 negm2 = make_float2(-m2, -m2);
-    float lsum = 0.f;
+    float2 ls2 = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
-      uint32_t s[32], pk[16];
-      tmem_ld32(tS + 32 * ch, s);
-      tmem_wait_ld();
+      const uint32_t k = (cls >> (2 * ch)) & 3u;
+      uint32_t pk[16];
+      if (k == 2u) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const int col = 32 * ch + e;
-        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, negm2);
-        const float p0 = (valid && col >= c_lo && col < c_hi) ? ex2(x.x) : 0.f;
-        const float p1 = (valid && col + 1 >= c_lo && col + 1 < c_hi) ? ex2(x.y) : 0.f;
-        lsum += p0 + p1;
-        pk[e >> 1] = pack16<FMT>(p0, p1);
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      } else {
+        uint32_t s[32];
+        tmem_ld32(tS + 32 * ch, s);
+        tmem_wait_ld();
+        if (k == 1u) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, negm2);
+            const float2 p = make_float2(ex2(x.x), ex2(x.y));
+            ls2 = __fadd2_rn(ls2, p);
+            pk[e >> 1] = pack16<FMT>(p.x, p.y);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int col = 32 * ch + e;
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, negm2);
+            const float p0 = (col >= r_lo && col < r_hi) ? ex2(x.x) : 0.f;
+            const float p1 = (col + 1 >= r_lo && col + 1 < r_hi) ? ex2(x.y) : 0.f;
+            ls2 = __fadd2_rn(ls2, make_float2(p0, p1));
+            pk[e >> 1] = pack16<FMT>(p0, p1);
+          }
+        }
       }
       tmem_st16(tS + 16 * ch, pk);     // P (16-bit) over the S columns already consumed
     }
+    const float lsum = ls2.x + ls2.y;
     tmem_wait_st();
     tc_fence_before();
     __syncthreads();
@@ -273,7 +359,7 @@ tc_win_fwd_kernel(const WinParams prm) {
       prm.l[gw * WD + slot] = lsum;
       prm.m[gw * WD + slot] = m2 * LN2;
     }
-    const float inv_l = valid ? 1.f / lsum : 0.f;
+    const float inv_l = valid ? 1.f / lsum : 0.f;      // rows no window maps to: O row is never scattered
     mbar_wait(bar_o, it & 1u);
     tc_fence_after();
 
@@ -347,7 +433,8 @@ template <int D> struct WBCfg {
   static constexpr int OFF_TOK = OFF_ROW + BMAXE * 4;        // int[128] token of every tile row
   static constexpr int OFF_STAT = OFF_TOK + 128 * 4;         // float nlse[128], a[128], b[128]
   static constexpr int OFF_AMAX = OFF_STAT + 3 * 128 * 4;    // uint[4]
-  static constexpr int OFF_BAR = OFF_AMAX + 16;
+  static constexpr int OFF_WIN = OFF_AMAX + 16;              // int4[128] window origins
+  static constexpr int OFF_BAR = OFF_WIN + 128 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
   static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;
   static constexpr int COL_T1 = 0, COL_T2 = 128, COL_DQ = 0;
@@ -389,6 +476,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
   float* sa = snl + 128;
   float* sb = snl + 256;
   unsigned int* samax = reinterpret_cast<unsigned int*>(sptr + C::OFF_AMAX);
+  int4* wininfo = reinterpret_cast<int4*>(sptr + C::OFF_WIN);
   const uint32_t bar_a = sbase + C::OFF_BAR, bar_b = bar_a + 8, tmem_slot = bar_a + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Geo& g = prm.g;
@@ -445,7 +533,9 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
   for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x) {
     const long long gw0 = grp * mp.nwc;
     if (tid < 4) samax[tid] = 0;
-    build_table(g, mp, gw0, prm.nwin, D, tsrc, trow, tid, 128, rowtok);
+    build_wininfo(g, mp, gw0, prm.nwin, wininfo, tid);
+    __syncthreads();
+    build_table(g, mp, wininfo, D, tsrc, trow, tid, 128, rowtok);
     __syncthreads();
 
     // ---- A: gather q, k, v, dy
@@ -458,24 +548,9 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
         const int ri = trow[e];
         uint32_t mx = 0;
         if (ri >= 0) {
-          const long long so = tsrc[e];
           const int rr = ri & 255;
           const uint32_t dst = sbase + (uint32_t)(x * C::TILE_BYTES + (rr >> 6) * C::BOX_BYTES + (rr & 7) * 2 + c0 * 128);
-          const uint32_t chunk = (uint32_t)((rr & 63) >> 3);
-          unsigned short v[CB];
-          if (so >= 0) {
-            const unsigned short* p = tens[x] + so + (long long)c0 * N;
-#pragma unroll
-            for (int j = 0; j < CB; ++j) v[j] = ldg_nc_u16(p + (long long)j * N);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CB; ++j) v[j] = 0;
-          }
-#pragma unroll
-          for (int j = 0; j < CB; ++j) {
-            sts_u16(dst + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4), v[j]);
-            if (INBF) mx = max(mx, (uint32_t)(v[j] & 0x7fff));
-          }
+          mx = gather_unit<CB>(tens[x] + (long long)c0 * N, tsrc[e], N, dst, (uint32_t)((rr & 63) >> 3));
         }
         if (INBF) {
           mx = __reduce_max_sync(0xffffffffu, mx);
