@@ -30,7 +30,7 @@ using namespace ptx;
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int MAXE = 1024;     // table entries per CTA iteration (32 warp-items)
+constexpr int MAXE = 640;      // table entries per CTA iteration (20 warp-items); sized so that 2 CTAs fit one SM
 constexpr int CB = 64;         // channels per gather / scatter unit (64 loads in flight per lane)
 
 template <int FMT> struct El { using type = __half; };
@@ -115,7 +115,10 @@ template <int D, int NT> struct WCfg {
   static constexpr int COLS_PER_TILE = (D == 64) ? 128 : 256;
   static constexpr int TMEM_COLS = COLS_PER_TILE * NT;
   static constexpr int COL_O = (D == 64) ? 64 : 128;         // P (64 cols) aliases S; O beside / after it
-  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS < 227 * 1024 / SMEM_BYTES ? 512 / TMEM_COLS : 227 * 1024 / SMEM_BYTES;
+  // 228 KB of shared memory per SM, 1 KB of it reserved per resident CTA
+  static constexpr int BY_SMEM = 228 * 1024 / (SMEM_BYTES + 1024);
+  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS < BY_SMEM ? 512 / TMEM_COLS : BY_SMEM;
+  static_assert(NT != 2 || D != 64 || CTAS_PER_SM == 2, "d = 64 pair kernel must fit twice per SM");
 };
 
 // ---- table: entry e = warp-item * 32 + lane  ->  (source element offset | -1, (tile << 8) | row | -1)
