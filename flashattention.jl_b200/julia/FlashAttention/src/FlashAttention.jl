@@ -23,4 +23,6 @@ include("circulant.jl")
 export dense_fa!, circulant_fa!
 export dense_fa, windowed_fa, circulant_fa, block_fa
 
+include("multigpu.jl")       # shard_batch, ring_dense_fa (not in the reference: SURVEY 8e)
+
 end
