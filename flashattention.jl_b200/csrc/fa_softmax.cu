@@ -54,13 +54,70 @@ __global__ void softmax_dim2_kernel(T* __restrict__ out, const T* __restrict__ i
   }
 }
 
+__device__ __forceinline__ void online_merge(float& mx, float& sum, float om, float os) {
+  const float mn = fmaxf(mx, om);
+  const float a = (mx == -INFINITY) ? 0.f : expf(mx - mn), b = (om == -INFINITY) ? 0.f : expf(om - mn);
+  sum = sum * a + os * b;
+  mx = mn;
+}
+
+// dim 1, few long columns (the vector case of bench/softmax.jl:8-35): one 1024-thread block per column.
+template <typename T>
+__global__ void softmax_dim1_block_kernel(T* __restrict__ out, const T* __restrict__ in, long long M) {
+  __shared__ float smx[32], ssum[32];
+  const T* x = in + (long long)blockIdx.x * M;
+  T* y = out + (long long)blockIdx.x * M;
+  float mx = -INFINITY, sum = 0.f;
+  for (long long i = threadIdx.x; i < M; i += blockDim.x) online_merge(mx, sum, to_f32<T>(x[i]), 1.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) online_merge(mx, sum, __shfl_xor_sync(0xffffffffu, mx, o), __shfl_xor_sync(0xffffffffu, sum, o));
+  if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; ssum[threadIdx.x >> 5] = sum; }
+  __syncthreads();
+  mx = -INFINITY; sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) online_merge(mx, sum, smx[w], ssum[w]);
+  const float inv = 1.f / sum;
+  for (long long i = threadIdx.x; i < M; i += blockDim.x) y[i] = from_f32<T>(expf(to_f32<T>(x[i]) - mx) * inv);
+}
+
+// dim 2, long rows: block = 8 consecutive rows x 128 slices of the strided N axis (a warp = 8 rows x 4
+// slices reads four full 32-byte sectors per load); (max, sum) reduced over the slices through smem.
+template <typename T>
+__global__ void softmax_dim2_sliced_kernel(T* __restrict__ out, const T* __restrict__ in, long long M, long long N, long long B) {
+  __shared__ float smx[128][8], ssum[128][8];
+  const int rx = threadIdx.x & 7, sy = threadIdx.x >> 3;
+  const long long groups = (M + 7) / 8;
+  for (long long gb = blockIdx.x; gb < groups * B; gb += gridDim.x) {
+    const long long b = gb / groups, i = (gb - b * groups) * 8 + rx;
+    const bool ok = i < M;
+    const T* x = in + b * M * N + i;
+    T* y = out + b * M * N + i;
+    float mx = -INFINITY, sum = 0.f;
+    if (ok) for (long long n = sy; n < N; n += 128) online_merge(mx, sum, to_f32<T>(x[n * M]), 1.f);
+    smx[sy][rx] = mx; ssum[sy][rx] = sum;
+    __syncthreads();
+    mx = -INFINITY; sum = 0.f;
+    for (int w = 0; w < 128; ++w) online_merge(mx, sum, smx[w][rx], ssum[w][rx]);
+    const float inv = 1.f / sum;
+    if (ok) for (long long n = sy; n < N; n += 128) y[n * M] = from_f32<T>(expf(to_f32<T>(x[n * M]) - mx) * inv);
+    __syncthreads();
+  }
+}
+
 template <typename T>
 int launch(void* out, const void* in, long long M, long long N, long long B, int dim, cudaStream_t st) {
   if (dim == 1) {
     const long long cols = N * B;
-    long long blocks = (cols + 7) / 8;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    softmax_dim1_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M, cols);
+    if (cols < 148 * 2 && M >= 4096) {      // few long columns: a block per column
+      softmax_dim1_block_kernel<T><<<(unsigned)cols, 1024, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M);
+    } else {
+      long long blocks = (cols + 7) / 8;
+      if (blocks > 148 * 32) blocks = 148 * 32;
+      softmax_dim1_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M, cols);
+    }
+  } else if (N >= 256) {                    // long strided rows: slice N across the block
+    long long blocks = ((M + 7) / 8) * B;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    softmax_dim2_sliced_kernel<T><<<(unsigned)blocks, 1024, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M, N, B);
   } else {
     long long blocks = (M * B + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;

@@ -59,14 +59,19 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // lazy rescale: P may grow to 2^8 b
 #endif
 constexpr int EMU_PER_32 = FA_EMU_PER_32;   // exponentials per 32 emulated on the FMA pipe (8 = 25 %)
 
-template <int D>
+// NQT = 128-query tiles per CTA.  2: one CTA per SM, 384 threads, all 512 TMEM columns -- the
+// tensor-bound dense configuration.  1: 256 threads, 256 TMEM columns and ~100 KB of smem, so TWO CTAs
+// share an SM and overlap each other's prologue (Q/K/V fetch latency) and epilogue (O store) -- the
+// short-loop circulant configuration, where a CTA lives for only (128 + W) / 64 key tiles.
+template <int D, int NQT = 2>
 struct Cfg {
-  static constexpr int K_STAGES = (D == 128) ? 3 : 4;
-  static constexpr int V_STAGES = (D == 128) ? 4 : 6;
+  static constexpr int THREADS = 128 + 128 * NQT;
+  static constexpr int K_STAGES = (NQT == 1) ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 4);
+  static constexpr int V_STAGES = (NQT == 1) ? ((D == 128) ? 3 : 6) : ((D == 128) ? 4 : 6);
   static constexpr int BOX_BYTES = 64 * D * 2;          // 64 tokens x D channels, 16-bit
   static constexpr int QTILE_BYTES = 2 * BOX_BYTES;     // 128 queries
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = 2 * QTILE_BYTES;
+  static constexpr int OFF_K = NQT * QTILE_BYTES;
   static constexpr int OFF_V = OFF_K + K_STAGES * BOX_BYTES;
   static constexpr int OFF_BAR = OFF_V + V_STAGES * BOX_BYTES;
   // barrier slots (8 B each)
@@ -82,7 +87,9 @@ struct Cfg {
   static constexpr int NUM_BARS = BAR_OFINAL + 2;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;   // + alignment slack
-  static constexpr int COL_S = 0, COL_O = 256;                   // S_t[b] = 128 t + 64 b; O_t = 256 + D t
+  static constexpr int TMEM_COLS = (NQT == 2) ? 512 : 256;
+  static constexpr int COL_S = 0, COL_O = 128 * NQT;             // S_t[b] = 128 t + 64 b; O_t = COL_O + D t
+  static constexpr int CTAS_PER_SM = (NQT == 2) ? 1 : 2;
 };
 
 struct TcParams {
@@ -99,12 +106,14 @@ __host__ __device__ inline int floor_div(int a, int b) { return (a >= 0) ? a / b
 struct TileRange { int jlo, jhi; };
 
 // key-tile stream of one CTA (a pair of 128-query tiles starting at q0), in 64-key tiles
+template <int NQT>
 __device__ __forceinline__ void tile_ranges(const TcParams& prm, int q0, int& kbase, int& nj, TileRange (&tr)[2]) {
+  tr[1].jlo = 0; tr[1].jhi = 0;
   if (prm.mode == MODE_CIRCULANT) {
     kbase = floor_div(q0 - prm.p, BN) * BN;
     nj = 0;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NQT; ++t) {
       const int i0 = q0 + 128 * t;
       if (i0 < prm.N) {
         tr[t].jlo = floor_div(i0 - prm.p - kbase, BN);
@@ -116,7 +125,7 @@ __device__ __forceinline__ void tile_ranges(const TcParams& prm, int q0, int& kb
     kbase = 0;
     nj = (prm.N + BN - 1) / BN;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NQT; ++t) {
       tr[t].jlo = 0;
       tr[t].jhi = (q0 + 128 * t < prm.N) ? nj : 0;
     }
@@ -130,11 +139,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int D, int FMT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int D, int FMT, int NQT>
+__global__ void __launch_bounds__(Cfg<D, NQT>::THREADS, Cfg<D, NQT>::CTAS_PER_SM)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
               const __grid_constant__ CUtensorMap tmv, const TcParams prm) {
-  using C = Cfg<D>;
+  using C = Cfg<D, NQT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase + C::OFF_Q, sK = sbase + C::OFF_K, sV = sbase + C::OFF_V;
@@ -143,21 +152,21 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
   const uint32_t tmem_slot = sbase + C::OFF_TMEM_SLOT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, b = blockIdx.y;
+  const int q0 = blockIdx.x * (128 * NQT), b = blockIdx.y;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) mbar_init(bar(C::BAR_QFULL + i), 1);
-    // K/V slots are released by BOTH MMA issuers (count 2)
-    for (int i = 0; i < C::K_STAGES; ++i) { mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), 2); }
-    for (int i = 0; i < C::V_STAGES; ++i) { mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), 2); }
+    // K/V slots are released by every MMA issuer (count NQT)
+    for (int i = 0; i < C::K_STAGES; ++i) { mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), NQT); }
+    for (int i = 0; i < C::V_STAGES; ++i) { mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), NQT); }
     for (int i = 0; i < 4; ++i) { mbar_init(bar(C::BAR_SFULL + i), 1); mbar_init(bar(C::BAR_PFULL + i), 128); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(C::BAR_ODONE + i), 1); mbar_init(bar(C::BAR_OFINAL + i), 1); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,14 +175,16 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
 
   int kbase, nj;
   TileRange tr[2];
-  tile_ranges(prm, q0, kbase, nj, tr);
+  tile_ranges<NQT>(prm, q0, kbase, nj, tr);
 
   if (warp < 4) {
-    setmaxnreg_dec<64>();
+    // register pool of the CTA = THREADS x launch registers (168 for NQT = 2, 128 for NQT = 1):
+    // 4 x 32 x 64 + 8 x 32 x 216 = 63488 <= 384 x 168;  4 x 32 x 56 + 4 x 32 x 200 = 32768 = 256 x 128
+    if (NQT == 2) setmaxnreg_dec<64>(); else setmaxnreg_dec<56>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < NQT; ++t) {
         if (tr[t].jhi > tr[t].jlo) {
           mbar_arrive_expect_tx(bar(C::BAR_QFULL + t), C::QTILE_BYTES);
           tma_load_3d(sQ + t * C::QTILE_BYTES, &tmq, bar(C::BAR_QFULL + t), q0 + 128 * t, 0, b);
@@ -190,7 +201,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
         mbar_arrive_expect_tx(bar(C::BAR_VFULL + sv), C::BOX_BYTES);
         tma_load_3d(sV + sv * C::BOX_BYTES, &tmv, bar(C::BAR_VFULL + sv), tok, 0, b);
       }
-    } else if (warp == 1 || warp == 3) {
+    } else if (warp == 1 || (warp == 3 && NQT == 2)) {
       // ------------------------------------------------------------ MMA issuer of Q tile t
       // The whole warp runs this loop (all values warp-uniform -> uniform registers); only the
       // tcgen05 instructions themselves are issued by one elected lane.
@@ -251,7 +262,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     }
   } else {
     // -------------------------------------------------------------- softmax warpgroups
-    setmaxnreg_inc<216>();
+    if (NQT == 2) setmaxnreg_inc<216>(); else setmaxnreg_inc<200>();
     const int t = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
@@ -445,7 +456,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -482,7 +493,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int dtype, long long N, int D, 
   return FA_OK;
 }
 
-template <int D, int FMT>
+template <int D, int FMT, int NQT>
 int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   CUtensorMap tmq, tmk, tmv;
   int rc;
@@ -494,10 +505,11 @@ int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.N = (int)g.N; prm.B = (int)g.B; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
   prm.scale_log2 = g.tau * LOG2E;
   prm.o_f32 = a.o_f32;
-  auto kern = tc_fwd_kernel<D, FMT>;
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM_BYTES));
-  const dim3 grid((unsigned)((g.N + 255) / 256), (unsigned)g.B);
-  kern<<<grid, TC_THREADS, Cfg<D>::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
+  using C = Cfg<D, NQT>;
+  auto kern = tc_fwd_kernel<D, FMT, NQT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const dim3 grid((unsigned)((g.N + 128 * NQT - 1) / (128 * NQT)), (unsigned)g.B);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
 }
@@ -524,8 +536,14 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
     set_error("tc_fwd: q/k/v must be 16-byte aligned"); return FA_ERR_INVALID;
   }
   const int fmt = dtype == FA_BF16 ? 1 : 0;
-  if (g.d == 128) return fmt ? launch_tc<128, 1>(g, a, dtype, st) : launch_tc<128, 0>(g, a, dtype, st);
-  return fmt ? launch_tc<64, 1>(g, a, dtype, st) : launch_tc<64, 0>(g, a, dtype, st);
+  // short key loops (circulant with a band of a few tiles): one Q tile per CTA, two CTAs per SM
+  const bool short_loop = g.mode == MODE_CIRCULANT && (256 + g.W) / 64 <= 24;
+  if (short_loop) {
+    if (g.d == 128) return fmt ? launch_tc<128, 1, 1>(g, a, dtype, st) : launch_tc<128, 0, 1>(g, a, dtype, st);
+    return fmt ? launch_tc<64, 1, 1>(g, a, dtype, st) : launch_tc<64, 0, 1>(g, a, dtype, st);
+  }
+  if (g.d == 128) return fmt ? launch_tc<128, 1, 2>(g, a, dtype, st) : launch_tc<128, 0, 2>(g, a, dtype, st);
+  return fmt ? launch_tc<64, 1, 2>(g, a, dtype, st) : launch_tc<64, 0, 2>(g, a, dtype, st);
 }
 
 }  // namespace fa

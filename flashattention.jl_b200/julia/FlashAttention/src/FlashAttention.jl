@@ -7,6 +7,7 @@ using Libdl
 using LinearAlgebra, SparseArrays
 using NNlib, MLUtils
 using CUDA
+using ChainRulesCore
 
 include("libfa.jl")          # library handle, dtype codes, status -> error()
 include("utils.jl")          # cartesian_circulant, circulant, window, unwindow   (reference src/utils.jl)
@@ -24,5 +25,6 @@ export dense_fa!, circulant_fa!
 export dense_fa, windowed_fa, circulant_fa, block_fa
 
 include("multigpu.jl")       # shard_batch, ring_dense_fa (not in the reference: SURVEY 8e)
+include("rrules.jl")         # ChainRulesCore.rrule for dense_fa / windowed_fa / circulant_fa (SURVEY 8f-1)
 
 end

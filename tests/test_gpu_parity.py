@@ -374,7 +374,7 @@ def test_naive_oracles_match_flash():
 
 # ------------------------------------------------------------------------------- softmax
 @pytest.mark.parametrize("dtype", [F32, BF16])
-@pytest.mark.parametrize("shape", [(7, 9, 3), (1000, 33, 2), (64, 4096)])
+@pytest.mark.parametrize("shape", [(7, 9, 3), (1000, 33, 2), (64, 4096), (70000, 1), (5000, 2, 3), (37, 1000, 2)])
 def test_fused_softmax(shape, dtype):
     S = randn_np(shape, 0, dtype)
     for dims in (1, 2):
@@ -399,3 +399,38 @@ def test_host_entry_points_match_device():
     yw_h = fa.windowed_fa(*(to_dev(t, F32, "cpu") for t in (q, k, v)), 7)[0]
     yw_d = fa.windowed_fa(*(to_dev(t) for t in (q, k, v)), 7)[0]
     assert torch.equal(yw_h.nan_to_num(7.0), yw_d.cpu().nan_to_num(7.0))
+
+
+# ------------------------------------------------------------------------------- rrules
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_autograd_wrappers_match_oracle_gradients(dtype):
+    """The forward/backward pairs as differentiable ops (what the Julia rrules bind): d/dq,k,v of
+    sum(y * g) through autograd equals the oracle backward."""
+    from fa_sm100a import autograd as fag
+    tol = tol_for(dtype)
+    # dense, 2-D spatial layout (flattened inside, reference src/dense.jl:6-8)
+    shape = (16, 8, 64, 2)
+    q, k, v, g = (randn_np(shape, s, dtype) for s in range(4))
+    Q, K, V = (to_dev(t, dtype).requires_grad_() for t in (q, k, v))
+    y = fag.dense_attention(Q, K, V)
+    (y.float() * to_dev(g, dtype).float()).sum().backward()
+    want = fo.dense_backward(*(t.astype(np.float64) for t in (q, k, v, g)))
+    for got, w in zip((Q.grad, K.grad, V.grad), want):
+        assert rel_err(to_np(got).reshape(w.shape, order="F"), w, dtype) < max(tol, 3e-3 if dtype == BF16 else 0)
+    # windowed 2-D and circulant 1-D
+    shape = (20, 12, 64, 2)
+    q, k, v, g = (randn_np(shape, s, dtype) for s in range(4))
+    Q, K, V = (to_dev(t, dtype).requires_grad_() for t in (q, k, v))
+    y = fag.windowed_attention(Q, K, V, 7)
+    (y.float().nan_to_num() * to_dev(g, dtype).float()).sum().backward()
+    want = fo.windowed_backward(*(t.astype(np.float64) for t in (q, k, v, g)), 7)
+    for got, w in zip((Q.grad, K.grad, V.grad), want):
+        assert rel_err(to_np(got), w, dtype) < tol
+    shape = (256, 64, 2)
+    q, k, v, g = (randn_np(shape, s, dtype) for s in range(4))
+    Q, K, V = (to_dev(t, dtype).requires_grad_() for t in (q, k, v))
+    y = fag.circulant_attention(Q, K, V, 33)
+    (y.float() * to_dev(g, dtype).float()).sum().backward()
+    want = fo.circulant_backward(*(t.astype(np.float64) for t in (q, k, v, g)), 33)
+    for got, w in zip((Q.grad, K.grad, V.grad), want):
+        assert rel_err(to_np(got), w, dtype) < max(tol, 3e-3 if dtype == BF16 else 0)
