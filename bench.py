@@ -82,7 +82,7 @@ def cpu_reference_tflops(steps, warmup, batch_sample):
     elements, all host cores as the reference's `@threads` would use (src/dense.jl:45)."""
     import numpy as np
     from oracle import c_oracle as co
-    cores = co.threads()
+    cores = co.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     rng = np.random.default_rng(0)
     q, k, v = (np.asfortranarray(rng.standard_normal((N, D, batch_sample), dtype=np.float32)) for _ in range(3))
     times = []

@@ -18,6 +18,7 @@ def lib():
         fp = ctypes.POINTER(ctypes.c_float)
         lg = ctypes.c_long
         _lib.fa_oracle_threads.restype = ctypes.c_int
+        _lib.fa_oracle_set_threads.argtypes = [ctypes.c_int]
         _lib.fa_oracle_dense_fwd.argtypes = [fp] * 6 + [lg] * 4
         _lib.fa_oracle_circulant_fwd.argtypes = [fp] * 6 + [lg] * 5
         _lib.fa_oracle_windowed_fwd.argtypes = [fp] * 6 + [ctypes.c_int, ctypes.POINTER(lg)] + [lg] * 6
@@ -26,6 +27,12 @@ def lib():
 
 def threads() -> int:
     return lib().fa_oracle_threads()
+
+
+def set_threads(n: int) -> int:
+    """Use ``n`` OpenMP threads (torchrun exports OMP_NUM_THREADS=1); returns the new count."""
+    lib().fa_oracle_set_threads(int(n))
+    return threads()
 
 
 def _f(x):

@@ -42,6 +42,16 @@ int fa_oracle_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 into every rank; the timed CPU baseline wants all host cores
+ * (the reference's Threads.@threads loop, src/dense.jl:45, uses every Julia thread). */
+void fa_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* P[i][j] = tau * sum_k Q[k][i] K[k][j];  Q, K are [d][ld] (token contiguous); P is [br][bc] */
 static void gemm_qkt(float* restrict P, const float* restrict Q, const float* restrict K, long br, long bc,
                      long d, long ldq, long ldk, float tau) {
