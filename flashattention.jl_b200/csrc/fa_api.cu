@@ -29,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
              int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st);
+int tmem_bw_probe(int mode, int nwarps, int iters, long long* out_dev, cudaStream_t st);
 
 namespace {
 
@@ -498,6 +499,14 @@ int fa_debug_umma_probe(int mode, const void* a, const void* b, const float* p, 
   int rc = need_device();
   if (rc) return rc;
   return tc_probe(mode, a, b, p, out, D, dtype, lbo, sbo, kstep, kbox, afmt, static_cast<cudaStream_t>(stream));
+}
+
+// TMEM read/write bandwidth microbenchmark (see fa_tc_probe.cu).  Not a product API.
+int fa_debug_tmem_bw(int mode, int nwarps, int iters, long long* out_dev, void* stream) {
+  int rc = need_device();
+  if (rc) return rc;
+  if ((nwarps != 1 && nwarps != 4 && nwarps != 8) || iters <= 0 || !out_dev) { set_error("bad probe arguments"); return FA_ERR_INVALID; }
+  return tmem_bw_probe(mode, nwarps, iters, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -110,7 +110,50 @@ probe_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
+// TMEM bandwidth probe: `nwarps` warps (4 or 8; warp w owns lane quarter w % 4) each issue `iters`
+// rounds of 4 x tcgen05.ld.32x32b.x32 (mode 0) or 4 x tcgen05.st.32x32b.x32 (mode 1) over 128 columns and
+// report elapsed SM clocks.  bytes moved = nwarps * iters * 4 * 4096.
+__global__ void tmem_bw_kernel(int mode, int iters, long long* out) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(smem_u32(&slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = threadIdx.x + i;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(base + 32 * c, r);
+        tmem_wait_ld();
+        acc += r[0] ^ r[31];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st32(base + 32 * c, r);
+      tmem_wait_st();
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x % 32 == 0) out[warp] = t1 - t0 + (acc == 0xdeadbeef ? 1 : 0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
 }  // namespace
+
+int tmem_bw_probe(int mode, int nwarps, int iters, long long* out_dev, cudaStream_t st) {
+  tmem_bw_kernel<<<1, 32 * nwarps, 0, st>>>(mode, iters, out_dev);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
 
 int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
              int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st) {
