@@ -48,16 +48,22 @@ constexpr int BW_THREADS = 384;
 constexpr int BT = 64;                      // streamed tokens per step (one TMA box)
 constexpr float LOG2E = 1.4426950408889634f;
 
-template <int D, int KIND>
+template <int D, int KIND, int OT = 0>
 struct BCfg {
   static constexpr int NS = (D == 128) ? 4 : 6;          // streamed stages
   static constexpr int BOX_BYTES = 64 * D * 2;           // 64 tokens x D channels, 16-bit
   static constexpr int OWN_BYTES = 2 * BOX_BYTES;        // 128 owner tokens of one tensor
   static constexpr int STAGE_BYTES = 2 * BOX_BYTES;      // Y1 box + Y2 box
   static constexpr int STAT_BYTES = 512;                 // nlse[64], ndelta[64] (KIND 0 only)
+  // KIND 1 keeps its owner tiles (Q, dO) in TMEM as K-major A operands: an SS-mode M=128, N=64 MMA
+  // reads 6 KB of shared memory per 32 clk of math (192 B/clk > the 128 B/clk port), a TS-mode one 2 KB.
+  // KIND 0 has no TMEM left for that (T1, T2 double-buffered + dV + dK = 512 columns at d = 128).
+  // (Dense only: with the few-step loops of a circulant band the synchronous owner load costs more
+  // than the SS-mode penalty, measured 1.34 vs 1.07 ms at C4.)
+  static constexpr bool OWN_TMEM = (KIND == 1) && (OT == 1);
   static constexpr int OFF_X1 = 0;
   static constexpr int OFF_X2 = OWN_BYTES;
-  static constexpr int OFF_Y = 2 * OWN_BYTES;
+  static constexpr int OFF_Y = OWN_TMEM ? 0 : 2 * OWN_BYTES;
   static constexpr int OFF_STAT = OFF_Y + NS * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_STAT + NS * STAT_BYTES;
   static constexpr int BAR_OWN = 0;
@@ -72,6 +78,7 @@ struct BCfg {
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;
   static constexpr int COL_T1 = 0, COL_T2 = 128, COL_ACC = 256;
+  static constexpr int COL_X = 384;                      // KIND 1: X1 at 384, X2 at 384 + D/2 (16-bit, K-major)
 };
 
 struct BwdParams {
@@ -80,6 +87,7 @@ struct BwdParams {
   const float* nlse;     // [B][Npad]
   const float* ndelta;   // [B][Npad]  (scaled by sv*sg when the inputs were re-encoded)
   const float* amax;     // device: max|q|, max|k|, max|v|, max|dO| of the re-encoded inputs, or NULL
+  const void *x1, *x2;   // KIND 1: owner tensors (Q, dO) as raw [B][D][N] pointers (loaded straight into TMEM)
   int N, Npad, W, p, mode;
   float scale_log2;      // tau * log2(e)
   float tau;
@@ -182,12 +190,12 @@ __global__ void bwd_prep_kernel(const T* __restrict__ o, const T* __restrict__ d
   }
 }
 
-template <int D, int FMT, int KIND, int OBF>
+template <int D, int FMT, int KIND, int OBF, int OT>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
               const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2,
               const BwdParams prm) {
-  using C = BCfg<D, KIND>;
+  using C = BCfg<D, KIND, OT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sX1 = sbase + C::OFF_X1, sX2 = sbase + C::OFF_X2, sY = sbase + C::OFF_Y;
@@ -204,7 +212,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
     prefetch_tensormap(&tmX1); prefetch_tensormap(&tmX2); prefetch_tensormap(&tmY1); prefetch_tensormap(&tmY2);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar(C::BAR_OWN), 1);
+    mbar_init(bar(C::BAR_OWN), C::OWN_TMEM ? 256 : 1);
     for (int i = 0; i < C::NS; ++i) { mbar_init(bar(C::BAR_FULL + i), 1); mbar_init(bar(C::BAR_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(C::BAR_T1 + i), 1); mbar_init(bar(C::BAR_T2 + i), 1);
@@ -236,11 +244,13 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
     setmaxnreg_dec<64>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
-      mbar_arrive_expect_tx(bar(C::BAR_OWN), 2 * C::OWN_BYTES);
-      tma_load_3d(sX1, &tmX1, bar(C::BAR_OWN), t0, 0, b);
-      tma_load_3d(sX1 + C::BOX_BYTES, &tmX1, bar(C::BAR_OWN), t0 + 64, 0, b);
-      tma_load_3d(sX2, &tmX2, bar(C::BAR_OWN), t0, 0, b);
-      tma_load_3d(sX2 + C::BOX_BYTES, &tmX2, bar(C::BAR_OWN), t0 + 64, 0, b);
+      if (!C::OWN_TMEM) {
+        mbar_arrive_expect_tx(bar(C::BAR_OWN), 2 * C::OWN_BYTES);
+        tma_load_3d(sX1, &tmX1, bar(C::BAR_OWN), t0, 0, b);
+        tma_load_3d(sX1 + C::BOX_BYTES, &tmX1, bar(C::BAR_OWN), t0 + 64, 0, b);
+        tma_load_3d(sX2, &tmX2, bar(C::BAR_OWN), t0, 0, b);
+        tma_load_3d(sX2 + C::BOX_BYTES, &tmX2, bar(C::BAR_OWN), t0 + 64, 0, b);
+      }
       for (int g = 0; g < ns; ++g) {
         const int s = g % C::NS;
         const int tok = circ ? (int)pmod(cbase + BT * g, prm.N) : BT * g;
@@ -255,7 +265,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       }
     } else if (warp == 1) {
       // ------------------------------------------------------------ MMA issuer (warp-uniform loop)
-      constexpr uint32_t idesc_t = make_idesc_f16(FMT, FMT, 1, 1, 128, BT);     // A, B MN-major
+      constexpr uint32_t idesc_t = make_idesc_f16(FMT, FMT, C::OWN_TMEM ? 0 : 1, 1, 128, BT);   // A MN-major smem (or TMEM), B MN-major
       constexpr uint32_t idesc_acc = make_idesc_f16(FMT, FMT, 0, 0, 128, D);    // A in TMEM, B K-major
       const uint64_t x1d = make_smem_desc_sw128(sX1, C::BOX_BYTES, 1024);
       const uint64_t x2d = make_smem_desc_sw128(sX2, C::BOX_BYTES, 1024);
@@ -272,12 +282,16 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
         const uint64_t y2 = y1 + (uint64_t)(C::BOX_BYTES >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tT1 + 64 * bb, x1d + (uint64_t)(ks * 128), y1 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            if (C::OWN_TMEM) mma_ts(tT1 + 64 * bb, tmem_base + C::COL_X + ks * 8, y1 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+            else mma_ss(tT1 + 64 * bb, x1d + (uint64_t)(ks * 128), y1 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+          }
           tc_commit(bar(C::BAR_T1 + bb));
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tT2 + 64 * bb, x2d + (uint64_t)(ks * 128), y2 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            if (C::OWN_TMEM) mma_ts(tT2 + 64 * bb, tmem_base + C::COL_X + D / 2 + ks * 8, y2 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+            else mma_ss(tT2 + 64 * bb, x2d + (uint64_t)(ks * 128), y2 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
+          }
           tc_commit(bar(C::BAR_T2 + bb));
         }
         __syncwarp();
@@ -333,6 +347,31 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       rnl = make_float2(a, a); rnd = make_float2(d, d);
     }
     const int WW = prm.W, pp = prm.p;
+
+    if (C::OWN_TMEM) {
+      // owner rows straight from global memory into TMEM (thread == row; a warp reads 32 consecutive
+      // tokens per channel): warpgroup 0 loads X1 (Q), warpgroup 1 loads X2 (dO); two channels per column
+      const unsigned short* src = static_cast<const unsigned short*>(wg == 0 ? prm.x1 : prm.x2) + (size_t)b * D * prm.N + row_tok;
+      const uint32_t tX = tmem_base + lane_addr + C::COL_X + wg * (D / 2);
+      const bool inr = row_tok < prm.N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 64) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          uint32_t lo = 0, hi = 0;
+          if (inr) {
+            lo = __ldg(src + (size_t)(c0 + 2 * i) * prm.N);
+            hi = __ldg(src + (size_t)(c0 + 2 * i + 1) * prm.N);
+          }
+          r[i] = lo | (hi << 16);
+        }
+        tmem_st32(tX + c0 / 2, r);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar(C::BAR_OWN));
+    }
 
     for (int j = wg; j < ns; j += 2) {
       const uint32_t par = (uint32_t)(j >> 1) & 1u;
@@ -447,21 +486,27 @@ int launch_tc_bwd(const Geo& g, const BwdArgs& a, const void* q, const void* k, 
   }
   BwdParams prm;
   prm.nlse = nlse; prm.ndelta = ndelta; prm.amax = amax;
+  prm.x1 = q; prm.x2 = d_o;
   prm.N = (int)g.N; prm.Npad = Npad; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
   prm.scale_log2 = g.tau * LOG2E; prm.tau = g.tau;
   const dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.B);
   {
-    auto kern = tc_bwd_kernel<D, FMT, 0, OBF>;
+    auto kern = tc_bwd_kernel<D, FMT, 0, OBF, 0>;
     FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<D, 0>::SMEM_BYTES));
     prm.out0 = a.dv; prm.out1 = a.dk;
     kern<<<grid, BW_THREADS, BCfg<D, 0>::SMEM_BYTES, st>>>(tk, tv, tq, tg, prm);
     FA_CUDA_TRY(cudaGetLastError());
   }
-  {
-    auto kern = tc_bwd_kernel<D, FMT, 1, OBF>;
-    FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<D, 1>::SMEM_BYTES));
-    prm.out0 = a.dq; prm.out1 = nullptr;
-    kern<<<grid, BW_THREADS, BCfg<D, 1>::SMEM_BYTES, st>>>(tq, tg, tk, tv, prm);
+  prm.out0 = a.dq; prm.out1 = nullptr;
+  if (g.mode == MODE_DENSE) {
+    auto kern = tc_bwd_kernel<D, FMT, 1, OBF, 1>;
+    FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<D, 1, 1>::SMEM_BYTES));
+    kern<<<grid, BW_THREADS, BCfg<D, 1, 1>::SMEM_BYTES, st>>>(tq, tg, tk, tv, prm);
+    FA_CUDA_TRY(cudaGetLastError());
+  } else {
+    auto kern = tc_bwd_kernel<D, FMT, 1, OBF, 0>;
+    FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<D, 1, 0>::SMEM_BYTES));
+    kern<<<grid, BW_THREADS, BCfg<D, 1, 0>::SMEM_BYTES, st>>>(tq, tg, tk, tv, prm);
     FA_CUDA_TRY(cudaGetLastError());
   }
   return FA_OK;
