@@ -143,7 +143,10 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
 // tensor-core backward (two deterministic kernels: key-owner dK/dV, query-owner dQ); same coverage
 bool tc_bwd_supported(const Geo& g, int dtype);
 size_t tc_bwd_workspace_bytes(const Geo& g, int dtype, int flags);
-int tc_bwd(const Geo& g, const BwdArgs& a, int dtype, int flags, void* workspace, cudaStream_t st);
+// out_f32: dq/dk/dv are float32 buffers whatever the input dtype (partials of the ring backward)
+int tc_bwd(const Geo& g, const BwdArgs& a, int dtype, int flags, void* workspace, cudaStream_t st, int out_f32 = 0);
+int merge_partials(float* oa, float* la, float* ma, const void* ob, const float* lb, const float* mb, void* out,
+                   long long N, int dv, long long B, int dtype, int blk_f32, int first, cudaStream_t st);
 
 // tensor-core windowed attention (one 128-row tile = floor(128 / W^D) windows): 16-bit dtypes,
 // d == dv in {64,128}, W^D <= 128

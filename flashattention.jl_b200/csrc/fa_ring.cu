@@ -99,6 +99,39 @@ int merge_t(float* oa, float* la, float* ma, const void* ob, const float* lb, co
 
 size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// acc = (first ? 0 : acc) + part      (fp32, grid-stride)
+__global__ void accumulate_kernel(float* __restrict__ acc, const float* __restrict__ part, size_t n, int first) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc[i] = (first ? 0.f : acc[i]) + part[i];
+}
+// part (in `dtype`) added into acc (fp32): the exact-fp32 SIMT fallback writes its gradients in `dtype`
+template <typename T>
+__global__ void accumulate_typed_kernel(float* __restrict__ acc, const T* __restrict__ part, size_t n, int first) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    acc[i] = (first ? 0.f : acc[i]) + to_f32<T>(part[i]);
+}
+template <typename T>
+__global__ void cast_out_kernel(T* __restrict__ out, const float* __restrict__ acc, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = from_f32<T>(acc[i]);
+}
+unsigned ew_blocks(size_t n) { const size_t b = (n + 255) / 256; return (unsigned)(b < 148 * 16 ? (b ? b : 1) : 148 * 16); }
+
+int accumulate(float* acc, const void* part, size_t n, int part_f32, int dtype, int first, cudaStream_t st) {
+  if (part_f32 || dtype == FA_F32) accumulate_kernel<<<ew_blocks(n), 256, 0, st>>>(acc, static_cast<const float*>(part), n, first);
+  else if (dtype == FA_F16) accumulate_typed_kernel<__half><<<ew_blocks(n), 256, 0, st>>>(acc, static_cast<const __half*>(part), n, first);
+  else accumulate_typed_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(acc, static_cast<const __nv_bfloat16*>(part), n, first);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+int cast_out(void* out, const float* acc, size_t n, int dtype, cudaStream_t st) {
+  if (dtype == FA_F32) { FA_CUDA_TRY(cudaMemcpyAsync(out, acc, n * 4, cudaMemcpyDeviceToDevice, st)); return FA_OK; }
+  if (dtype == FA_F16) cast_out_kernel<__half><<<ew_blocks(n), 256, 0, st>>>(static_cast<__half*>(out), acc, n);
+  else cast_out_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(static_cast<__nv_bfloat16*>(out), acc, n);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
 }  // namespace
 
 // blk_f32: the block partial is float32 although `dtype` (the type of `out`) is 16-bit
@@ -225,6 +258,135 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_compute[i]); cudaEventDestroy(ev_comm[i]); }
     cudaEventDestroy(ev_start);
     cudaStreamDestroy(xs);       // deferred by the runtime until its work has drained
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------ ring backward
+// Layout of the workspace (all 256-byte aligned):
+//   kbuf[2], vbuf[2]        K/V blocks in flight (dtype)
+//   kacc[2], vacc[2]        fp32 dK/dV accumulators that TRAVEL WITH their K/V block round the ring
+//   pq, pk, pv              fp32 partial gradients of the current step
+//   qacc                    fp32 dQ accumulator of the local queries
+//   bws                     workspace of the per-block backward (fa_workspace_bytes_dense_bwd)
+size_t fa_workspace_bytes_ring_dense_bwd(int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype, int flags) {
+  if (Nl <= 0 || d <= 0 || dv <= 0 || B <= 0) return 0;
+  const size_t esz = dtype_size(dtype);
+  const size_t kb = a256((size_t)Nl * d * B * esz), vb = a256((size_t)Nl * dv * B * esz);
+  const size_t k4 = a256((size_t)Nl * d * B * 4), v4 = a256((size_t)Nl * dv * B * 4);
+  return 2 * kb + 2 * vb + 2 * k4 + 2 * v4 + (2 * k4 + v4) + k4 + a256(fa_workspace_bytes_dense_bwd(Nl, d, dv, B, dtype, flags));
+}
+
+/* Ring attention backward ("backward rotates dK/dV accumulators with K/V").  Rank r holds the
+ * (Nl, ., B) shards of q, k, v, o, dO and the GLOBAL statistics l, m of its queries (from
+ * fa_ring_dense_fwd).  Step s: flash backward of the local queries against the resident block (rank
+ * (r - s) mod G): dQ += partial; the block's dK/dV accumulators (which arrived with it) += partials; then
+ * the accumulators are sent on.  After G steps every block's accumulators are back at their owner. */
+int fa_ring_dense_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                      const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                      int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype, int flags,
+                      void* nccl_comm, int rank, int nranks, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !k || !v || !o || !d_o || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (Nl <= 0 || d <= 0 || dv <= 0 || B <= 0 || B > 65535 || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bad ring arguments"); return FA_ERR_INVALID; }
+  if (dtype != FA_F32 && dtype != FA_F16 && dtype != FA_BF16) { set_error("bad dtype"); return FA_ERR_INVALID; }
+  if (nranks > 1 && !nccl_comm) { set_error("ring attention over %d ranks needs an NCCL communicator", nranks); return FA_ERR_INVALID; }
+  if (!workspace || workspace_bytes < fa_workspace_bytes_ring_dense_bwd(Nl, d, dv, B, dtype, flags)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); set_error("no CUDA device available (libfa_sm100a has no CPU fallback)"); return FA_ERR_CUDA; }
+  const NcclApi& nc = nccl_api();
+  if (nranks > 1 && !nc.ok) { set_error("libnccl.so.2 (ncclSend/ncclRecv) could not be resolved"); return FA_ERR_CUDA; }
+
+  const size_t esz = dtype_size(dtype);
+  const size_t nk = (size_t)Nl * d * B, nv = (size_t)Nl * dv * B;
+  const size_t kb = a256(nk * esz), vb = a256(nv * esz), k4 = a256(nk * 4), v4 = a256(nv * 4);
+  char* ws = static_cast<char*>(workspace);
+  void* kbuf[2] = {ws, ws + kb};                      ws += 2 * kb;
+  void* vbuf[2] = {ws, ws + vb};                      ws += 2 * vb;
+  float* kacc[2] = {reinterpret_cast<float*>(ws), reinterpret_cast<float*>(ws + k4)};  ws += 2 * k4;
+  float* vacc[2] = {reinterpret_cast<float*>(ws), reinterpret_cast<float*>(ws + v4)};  ws += 2 * v4;
+  float* pq = reinterpret_cast<float*>(ws);           ws += k4;
+  float* pk = reinterpret_cast<float*>(ws);           ws += k4;
+  float* pv = reinterpret_cast<float*>(ws);           ws += v4;
+  float* qacc = reinterpret_cast<float*>(ws);         ws += k4;
+  void* bws = ws;
+  const size_t bws_bytes = fa_workspace_bytes_dense_bwd(Nl, d, dv, B, dtype, flags);
+
+  Geo gd;
+  memset(&gd, 0, sizeof(gd));
+  gd.mode = MODE_DENSE; gd.d = (int)d; gd.dv = (int)dv; gd.N = Nl; gd.B = B; gd.tau = 1.0f / sqrtf((float)d);
+  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(gd, dtype);
+
+  cudaStream_t cs = static_cast<cudaStream_t>(stream), xs = nullptr;
+  cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_kv[2] = {nullptr, nullptr}, ev_acc_ready = nullptr, ev_acc_recv = nullptr, ev_start = nullptr;
+  if (nranks > 1) {
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_compute[i], cudaEventDisableTiming));
+      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_kv[i], cudaEventDisableTiming));
+    }
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_acc_ready, cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_acc_recv, cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventRecord(ev_start, cs));
+    FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_start, 0));
+  }
+  const int next = (rank + 1) % nranks, prev = (rank + nranks - 1) % nranks;
+  const ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+  const void* cur_k = k;
+  const void* cur_v = v;
+  int rc = FA_OK;
+  for (int s = 0; s < nranks && rc == FA_OK; ++s) {
+    const int bi = s & 1;
+    if (s + 1 < nranks) {        // K/V of the next step: overlapped with this step's compute
+      if (s >= 1) FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_compute[(s - 1) & 1], 0));
+      FA_NCCL_TRY(nc.GroupStart());
+      FA_NCCL_TRY(nc.Send(cur_k, nk * esz, ncclUint8, next, comm, xs));
+      FA_NCCL_TRY(nc.Send(cur_v, nv * esz, ncclUint8, next, comm, xs));
+      FA_NCCL_TRY(nc.Recv(kbuf[bi], nk * esz, ncclUint8, prev, comm, xs));
+      FA_NCCL_TRY(nc.Recv(vbuf[bi], nv * esz, ncclUint8, prev, comm, xs));
+      FA_NCCL_TRY(nc.GroupEnd());
+      FA_CUDA_TRY(cudaEventRecord(ev_kv[bi], xs));
+    }
+    // partial gradients of (local queries) x (resident block)
+    BwdArgs a{q, cur_k, cur_v, o, d_o, l, m, pq, pk, pv, nullptr, nullptr, nullptr, static_cast<float*>(bws)};
+    if (tc) { set_path("tc"); rc = tc_bwd(gd, a, dtype, flags, bws, cs, /*out_f32=*/1); }
+    else rc = fa_dense_bwd(q, cur_k, cur_v, o, d_o, l, m, pq, pk, pv, Nl, d, dv, B, dtype, flags, bws, bws_bytes, cs);
+    if (rc) break;
+    const int pf32 = tc ? 1 : 0;
+    if ((rc = accumulate(qacc, pq, nk, pf32, dtype, s == 0, cs))) break;
+    // this block's travelling accumulators: fresh at step 0, otherwise they arrived from the previous rank
+    if (s >= 1) FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_acc_recv, 0));
+    if ((rc = accumulate(kacc[bi], pk, nk, pf32, dtype, s == 0, cs))) break;
+    if ((rc = accumulate(vacc[bi], pv, nv, pf32, dtype, s == 0, cs))) break;
+    if (nranks > 1) {
+      FA_CUDA_TRY(cudaEventRecord(ev_compute[bi], cs));
+      FA_CUDA_TRY(cudaEventRecord(ev_acc_ready, cs));
+      FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_acc_ready, 0));
+      FA_NCCL_TRY(nc.GroupStart());
+      FA_NCCL_TRY(nc.Send(kacc[bi], nk * 4, ncclUint8, next, comm, xs));
+      FA_NCCL_TRY(nc.Send(vacc[bi], nv * 4, ncclUint8, next, comm, xs));
+      FA_NCCL_TRY(nc.Recv(kacc[bi ^ 1], nk * 4, ncclUint8, prev, comm, xs));
+      FA_NCCL_TRY(nc.Recv(vacc[bi ^ 1], nv * 4, ncclUint8, prev, comm, xs));
+      FA_NCCL_TRY(nc.GroupEnd());
+      FA_CUDA_TRY(cudaEventRecord(ev_acc_recv, xs));
+      if (s + 1 < nranks) {
+        FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_kv[bi], 0));
+        cur_k = kbuf[bi];
+        cur_v = vbuf[bi];
+      }
+    }
+  }
+  if (rc == FA_OK) {
+    // after the last exchange the accumulators of MY block are in buffer (nranks & 1); one rank: buffer 0
+    const int fin = nranks > 1 ? (nranks & 1) : 0;
+    if (nranks > 1) FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_acc_recv, 0));
+    if (!(rc = cast_out(dq, qacc, nk, dtype, cs)) && !(rc = cast_out(dk, kacc[fin], nk, dtype, cs)))
+      rc = cast_out(dv_out, vacc[fin], nv, dtype, cs);
+  }
+  if (nranks > 1) {
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_compute[i]); cudaEventDestroy(ev_kv[i]); }
+    cudaEventDestroy(ev_acc_ready); cudaEventDestroy(ev_acc_recv); cudaEventDestroy(ev_start);
+    cudaStreamDestroy(xs);
   }
   return rc;
 }

@@ -87,6 +87,7 @@ struct BwdParams {
   const float* nlse;     // [B][Npad]
   const float* ndelta;   // [B][Npad]  (scaled by sv*sg when the inputs were re-encoded)
   const float* amax;     // device: max|q|, max|k|, max|v|, max|dO| of the re-encoded inputs, or NULL
+  int out_f32;           // gradients stored as float32 whatever the input dtype (partials of the ring pass)
   const void *x1, *x2;   // KIND 1: owner tensors (Q, dO) as raw [B][D][N] pointers (loaded straight into TMEM)
   int N, Npad, W, p, mode;
   float scale_log2;      // tau * log2(e)
@@ -449,15 +450,21 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
     // dV = P^T (dO sg) / sg;  dK = tau dS'^T (Q sq) / (sv sg sq);  dQ = tau dS' (K sk) / (sv sg sk),  dS' = dS sv sg
     const float mul = (KIND == 0 && wg == 0) ? 1.f / sg : prm.tau / (sv * sg * (KIND == 0 ? sq : sk));
     const int c_lo = (KIND == 1) ? wg * (D / 64) : 0, c_hi = (KIND == 1) ? (wg + 1) * (D / 64) : D / 32;
+    float* outf = static_cast<float*>((KIND == 0 && wg == 1) ? prm.out1 : prm.out0) + (size_t)b * D * prm.N + row_tok;
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; ++c) {
       uint32_t o[32];
       tmem_ld32(tacc + 32 * c, o);
       tmem_wait_ld();
       if (in_range) {
+        if (prm.out_f32) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          out[(size_t)(32 * c + e) * prm.N] = from_f32<OT>(__uint_as_float(o[e]) * mul);
+          for (int e = 0; e < 32; ++e) outf[(size_t)(32 * c + e) * prm.N] = __uint_as_float(o[e]) * mul;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            out[(size_t)(32 * c + e) * prm.N] = from_f32<OT>(__uint_as_float(o[e]) * mul);
+        }
       }
     }
   }
@@ -469,7 +476,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
 
 template <int D, int FMT, int OBF>
 int launch_tc_bwd(const Geo& g, const BwdArgs& a, const void* q, const void* k, const void* v, const void* d_o,
-                  const float* amax, float* nlse, float* ndelta, int Npad, cudaStream_t st) {
+                  const float* amax, float* nlse, float* ndelta, int Npad, int out_f32, cudaStream_t st) {
   const int mma_dtype = FMT ? FA_BF16 : FA_F16;
   CUtensorMap tq, tk, tv, tg;
   int rc;
@@ -486,7 +493,7 @@ int launch_tc_bwd(const Geo& g, const BwdArgs& a, const void* q, const void* k, 
   }
   BwdParams prm;
   prm.nlse = nlse; prm.ndelta = ndelta; prm.amax = amax;
-  prm.x1 = q; prm.x2 = d_o;
+  prm.x1 = q; prm.x2 = d_o; prm.out_f32 = out_f32;
   prm.N = (int)g.N; prm.Npad = Npad; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
   prm.scale_log2 = g.tau * LOG2E; prm.tau = g.tau;
   const dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.B);
@@ -526,7 +533,7 @@ size_t tc_bwd_workspace_bytes(const Geo& g, int dtype, int flags) {
   return bytes;
 }
 
-int tc_bwd(const Geo& g, const BwdArgs& a, int dtype, int flags, void* workspace, cudaStream_t st) {
+int tc_bwd(const Geo& g, const BwdArgs& a, int dtype, int flags, void* workspace, cudaStream_t st, int out_f32) {
   if (!tc_bwd_supported(g, dtype)) { set_error("tc_bwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) |
        reinterpret_cast<uintptr_t>(a.d_o) | reinterpret_cast<uintptr_t>(workspace)) & 15) {
@@ -560,12 +567,12 @@ int tc_bwd(const Geo& g, const BwdArgs& a, int dtype, int flags, void* workspace
   const float* am = reencode ? amax : nullptr;
   const int sel = (g.d == 128 ? 4 : 0) | (dtype == FA_BF16 ? 2 : 0) | ((dtype == FA_BF16 && !reencode) ? 1 : 0);
   switch (sel) {   // D, caller dtype, MMA format
-    case 4 | 2 | 1: return launch_tc_bwd<128, 1, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, st);
-    case 4 | 2:     return launch_tc_bwd<128, 0, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, st);
-    case 4:         return launch_tc_bwd<128, 0, 0>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, st);
-    case 2 | 1:     return launch_tc_bwd<64, 1, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, st);
-    case 2:         return launch_tc_bwd<64, 0, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, st);
-    default:        return launch_tc_bwd<64, 0, 0>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, st);
+    case 4 | 2 | 1: return launch_tc_bwd<128, 1, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, out_f32, st);
+    case 4 | 2:     return launch_tc_bwd<128, 0, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, out_f32, st);
+    case 4:         return launch_tc_bwd<128, 0, 0>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, out_f32, st);
+    case 2 | 1:     return launch_tc_bwd<64, 1, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, out_f32, st);
+    case 2:         return launch_tc_bwd<64, 0, 1>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, out_f32, st);
+    default:        return launch_tc_bwd<64, 0, 0>(g, a, q, k, v, d_o, am, nlse, ndelta, Npad, out_f32, st);
   }
 }
 

@@ -33,7 +33,7 @@ __all__ = [
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
     "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys",
-    "dense_dpa", "windowed_dpa", "block_dpa", "circulant_dpa", "shard_batch", "ring_dense_fa",
+    "dense_dpa", "windowed_dpa", "block_dpa", "circulant_dpa", "shard_batch", "ring_dense_fa", "ring_dense_fa_backward",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -86,6 +86,8 @@ def _load():
         "fa_merge_partials": (ci, [vp] * 7 + [i64, i64, i64, ci, ci, vp]),
         "fa_workspace_bytes_ring_dense_fwd": (sz, [i64, i64, i64, i64, ci]),
         "fa_ring_dense_fwd": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, vp, ci, ci, vp, sz, vp]),
+        "fa_workspace_bytes_ring_dense_bwd": (sz, [i64, i64, i64, i64, ci, ci]),
+        "fa_ring_dense_bwd": (ci, [vp] * 10 + [i64, i64, i64, i64, ci, ci, vp, ci, ci, vp, sz, vp]),
         "fa_debug_umma_probe": (ci, [ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -101,7 +103,7 @@ EXPORTED_SYMBOLS = (
     "fa_workspace_bytes_circulant_bwd fa_circulant_bwd fa_workspace_bytes_windowed_fwd fa_windowed_fwd "
     "fa_workspace_bytes_windowed_bwd fa_windowed_bwd fa_window fa_unwindow fa_softmax fa_dense_fwd_host "
     "fa_circulant_fwd_host fa_windowed_fwd_host fa_release_host_staging fa_shard_batch fa_merge_partials "
-    "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd").split()
+    "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd").split()
 
 
 def _check(rc: int, what: str):
@@ -311,6 +313,32 @@ def ring_dense_fa(q, k, v, group=None, flags: int = 0):
                                      comm, rank, world, _ptr(ws), ws.numel(), _stream(q)), "fa_ring_dense_fwd")
         torch.cuda.current_stream(q.device).synchronize()    # the workspace dies with this frame
     return O, l, m
+
+
+def ring_dense_fa_backward(q, k, v, O, dO, l, m, group=None, flags: int = 0):
+    """Backward of :func:`ring_dense_fa`: every rank passes its token shards and the ``(O, l, m)`` the ring
+    forward returned and gets ``(dq, dk, dv)`` of its shard; dK/dV accumulators travel with the K/V blocks
+    (``fa_ring_dense_bwd``)."""
+    import torch.distributed as dist
+    _same(q, k, v, O, dO)
+    q, k, v, O, dO = (jl_array(t) for t in (q, k, v, O, dO))
+    l, m = (jl_array(t, torch.float32) for t in (l, m))
+    Nl, d, B = (int(s) for s in q.shape)
+    dv = int(v.shape[1])
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    comm = None
+    if world > 1:
+        dist.barrier(group)
+        comm = ctypes.c_void_p(_nccl_comm_ptr(group, q.device))
+    dq, dk, dvv = (jl_empty(t.shape, t.dtype, t.device) for t in (q, k, v))
+    ws = _workspace(lib.fa_workspace_bytes_ring_dense_bwd(Nl, d, dv, B, _dt(q), flags), q.device)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_ring_dense_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(O), _ptr(dO), _ptr(l), _ptr(m),
+                                     _ptr(dq), _ptr(dk), _ptr(dvv), Nl, d, dv, B, _dt(q), flags,
+                                     comm, rank, world, _ptr(ws), ws.numel(), _stream(q)), "fa_ring_dense_bwd")
+        torch.cuda.current_stream(q.device).synchronize()
+    return dq, dk, dvv
 
 
 # --------------------------------------------------------------------------------------------

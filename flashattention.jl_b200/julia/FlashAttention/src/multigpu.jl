@@ -37,3 +37,25 @@ function ring_dense_fa(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T, 3}, com
     CUDA.synchronize()          # the workspace must outlive the enqueued work
     return O, l, m
 end
+
+"Backward of `ring_dense_fa`: pass the shards and the `(O, l, m)` the ring forward returned."
+function ring_dense_fa_backward(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T, 3}, O::CuArray{T, 3}, dO::CuArray{T, 3},
+                                l::CuArray{Float32, 3}, m::CuArray{Float32, 3}, comm::Ptr{Cvoid},
+                                rank::Integer, nranks::Integer; flags::Integer=0) where {T}
+    Nl, d, batchsize = size(q)
+    dv = size(v, 2)
+    dQ, dK, dV = similar(q), similar(k), similar(v)
+    nws = ccall(sym(:fa_workspace_bytes_ring_dense_bwd), Csize_t, (Int64, Int64, Int64, Int64, Cint, Cint),
+                Nl, d, dv, batchsize, fa_dtype(T), Cint(flags))
+    ws = CuArray{UInt8}(undef, max(nws, 256))
+    rc = ccall(sym(:fa_ring_dense_bwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cint, Cint,
+                Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+               devptr(q), devptr(k), devptr(v), devptr(O), devptr(dO), devptr(l), devptr(m),
+               devptr(dQ), devptr(dK), devptr(dV), Nl, d, dv, batchsize, fa_dtype(T), Cint(flags),
+               comm, Cint(rank), Cint(nranks), devptr(ws), length(ws), current_stream())
+    check(rc, "fa_ring_dense_bwd")
+    CUDA.synchronize()
+    return dQ, dK, dV
+end

@@ -161,6 +161,17 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
                       void* nccl_comm, int rank, int nranks, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Ring attention backward: rank r passes its shards of q, k, v, o, dO and the GLOBAL l, m of its queries
+ * (outputs of fa_ring_dense_fwd) and receives dq, dk, dv of its shard.  Every step runs the flash backward
+ * of the local queries against the resident K/V block; the block's fp32 dK/dV accumulators travel round
+ * the ring with it (ncclSend/ncclRecv), the K/V exchange of the next step overlaps the compute. */
+size_t fa_workspace_bytes_ring_dense_bwd(int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype, int flags);
+int fa_ring_dense_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                      const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                      int64_t Nl, int64_t d, int64_t dv, int64_t B, int dtype, int flags,
+                      void* nccl_comm, int rank, int nranks, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* The *_host entry points keep their device staging buffers between calls (grow-only, per device);
  * this frees them.  Returns FA_OK. */
 int fa_release_host_staging(void);

@@ -107,6 +107,20 @@ def test_ring_single_rank_equals_dense(dtype, N, d):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype,N,d", [(torch.bfloat16, 512, 128), (torch.float32, 200, 32)])
+def test_ring_backward_single_rank_equals_dense(dtype, N, d):
+    import fa_sm100a as fa
+    q, k, v, g = (randn_np((N, d, 2), s, dtype) for s in range(4))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    O, l, m = fa.ring_dense_fa(Q, K, V)
+    got = fa.ring_dense_fa_backward(Q, K, V, O, G, l, m)
+    want = fo.dense_fa_backward_blocked(*(t.astype(np.float64) for t in (q, k, v)), to_np(O), g.astype(np.float64), to_np(l), to_np(m))
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    for a, b in zip(got, want):
+        assert rel_err(to_np(a), b, dtype) < tol
+
+
+@pytest.mark.gpu
 def test_merge_partials_kernel():
     import ctypes
     import fa_sm100a as fa
@@ -125,7 +139,7 @@ def test_merge_partials_kernel():
     assert rel_err(to_np(out), want[0]) < 1e-5 and rel_err(to_np(d[1]), want[1]) < 1e-5 and rel_err(to_np(d[2]), want[2]) < 1e-6
 
 
-def _nccl_ring_worker(rank, world, port, q, k, v, dtype, out):
+def _nccl_ring_worker(rank, world, port, q, k, v, dtype, out, g=None):
     sys.path.insert(0, os.path.join(ROOT, "flashattention.jl_b200"))
     import fa_sm100a as fa
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -134,8 +148,10 @@ def _nccl_ring_worker(rank, world, port, q, k, v, dtype, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     n = q.shape[0] // world
     sh = lambda t: fa.jl_array(np.asfortranarray(t[rank * n:(rank + 1) * n]), dtype=dtype, device=f"cuda:{rank}")
-    O, l, m = fa.ring_dense_fa(sh(q), sh(k), sh(v))
-    out[rank] = (O.float().cpu(), l.cpu(), m.cpu())
+    Q, K, V = sh(q), sh(k), sh(v)
+    O, l, m = fa.ring_dense_fa(Q, K, V)
+    grads = fa.ring_dense_fa_backward(Q, K, V, O, sh(g), l, m) if g is not None else ()
+    out[rank] = (O.float().cpu(), l.cpu(), m.cpu()) + tuple(x.float().cpu() for x in grads)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -157,3 +173,24 @@ def test_ring_two_ranks_nccl(dtype):
     tol = 1e-5 if dtype == torch.float32 else 2e-3
     assert rel_err(y, y0, dtype) < tol
     assert rel_err(l * np.exp(m - m0), l0) < tol         # l is tied to its m
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("dtype,world", [(torch.bfloat16, 2), (torch.float32, 2)] + ([(torch.bfloat16, 4)] if torch.cuda.device_count() >= 4 else []))
+def test_ring_backward_nccl(dtype, world):
+    """dK/dV accumulators travelling with the K/V blocks over NCCL: every rank's (dq, dk, dv) shard against
+    the oracle backward on the whole sequence (given the forward results the ranks computed)."""
+    N, d, B = (1024, 128, 2) if dtype == torch.bfloat16 else (256, 32, 2)
+    q, k, v, g = (randn_np((N, d, B), s, dtype) for s in range(4))
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_ring_worker, args=(world, port, q, k, v, dtype, out, g), nprocs=world, join=True)
+    cat = lambda i: np.concatenate([out[r][i].numpy() for r in range(world)])
+    O, l, m = cat(0), cat(1), cat(2)
+    want = fo.dense_fa_backward_blocked(*(t.astype(np.float64) for t in (q, k, v)), O.astype(np.float64), g.astype(np.float64),
+                                        l.astype(np.float64), m.astype(np.float64))
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    for i, w in zip((3, 4, 5), want):
+        assert rel_err(cat(i), w, dtype) < tol
