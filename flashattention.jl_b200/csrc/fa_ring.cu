@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
+#include <mutex>
 
 #include "fa_common.cuh"
 
@@ -30,9 +31,8 @@ struct NcclApi {
 
 const NcclApi& nccl_api() {
   static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy already in the process
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW);
@@ -44,7 +44,7 @@ const NcclApi& nccl_api() {
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
       api.ok = api.Send && api.Recv && api.GroupStart && api.GroupEnd;
     }
-  }
+  });
   return api;
 }
 

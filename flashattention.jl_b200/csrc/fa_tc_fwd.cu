@@ -32,6 +32,7 @@
 // TMEM columns: S_t[b] at 128 t + 64 b (64 fp32 columns each), O_t at 256 + d t; P_t(j) aliases
 // the first 32 columns of S_t[j&1].
 #include <cuda.h>
+#include <mutex>
 #include "fa_common.cuh"
 #include "fa_ptx.cuh"
 
@@ -466,15 +467,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+  });
   return fn;
 }
 

@@ -203,7 +203,8 @@ def test_circulant_fwd_fp32(N, d, B, W):
 
 @pytest.mark.parametrize("dtype", [BF16, F16])
 @pytest.mark.parametrize("N,d,B,W", [(1024, 64, 2, 255), (512, 128, 1, 129), (512, 64, 2, 64), (256, 64, 1, 256),
-                                     (384, 64, 1, 5), (2048, 64, 1, 1023), (128, 128, 2, 33)])
+                                     (384, 64, 1, 5), (2048, 64, 1, 1023), (128, 128, 2, 33),
+                                     (4096, 64, 1, 2049)])      # W > 1280: the two-Q-tile (NQT = 2) band kernel
 def test_circulant_fwd_tc(N, d, B, W, dtype):
     Q, K, V = _qkv((N, d, B), d, dtype)
     O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (Q, K, V)), W)
