@@ -32,7 +32,7 @@ __all__ = [
     "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
-    "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys",
+    "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys", "circulant", "batch_circulant",
     "dense_dpa", "windowed_dpa", "block_dpa", "circulant_dpa", "shard_batch", "ring_dense_fa", "ring_dense_fa_backward",
 ]
 
@@ -530,6 +530,35 @@ def circulant_keys(N: int, W: int) -> torch.Tensor:
     buf = (ctypes.c_int64 * (N * W))()
     _check(lib.fa_circulant_index(N, W, buf), "fa_circulant_index")
     return torch.tensor(list(buf), dtype=torch.int64).reshape(N, W).permute(1, 0)
+
+
+def circulant(V_or_N, M: Optional[int] = None, dtype=torch.float64):
+    """``circulant(N, M)`` / ``circulant(V)`` (src/utils.jl:19-31): the ``N x N`` banded periodic matrix in
+    CSC form whose column ``j`` holds ``V[:, j]`` (or ones) at the rows ``first(cartesian_circulant(., N, M))``;
+    returned as a ``torch.sparse_csc_tensor`` (row indices in the reference's storage order)."""
+    if isinstance(V_or_N, int):
+        N, vals = int(V_or_N), None
+    else:
+        V = V_or_N
+        M, N = int(V.shape[0]), int(V.shape[1])
+        vals = V.t().reshape(-1).to("cpu")                                 # column-major reshape(V, :)
+    rows = circulant_keys(N, int(M)).t().reshape(-1)                       # (W, N) column-major -> nz order
+    colptr = torch.arange(0, N + 1, dtype=torch.int64) * int(M)
+    if vals is None:
+        vals = torch.ones(N * int(M), dtype=dtype)
+    return torch.sparse_csc_tensor(colptr, rows, vals, size=(N, N))
+
+
+def batch_circulant(bV: torch.Tensor):
+    """``batch_circulant(bV)`` (src/utils.jl:33): block-diagonal of ``circulant(bV[:, :, b])``, as a
+    ``(B*N, B*N)`` sparse COO tensor."""
+    M, N, B = (int(s) for s in bV.shape)
+    idx, val = [], []
+    for b in range(B):
+        c = circulant(bV[:, :, b]).to_sparse_coo().coalesce()
+        idx.append(c.indices() + b * N)
+        val.append(c.values())
+    return torch.sparse_coo_tensor(torch.cat(idx, 1), torch.cat(val), (B * N, B * N)).coalesce()
 
 
 # --------------------------------------------------------------------------------------------

@@ -93,3 +93,30 @@ def test_julia_layout_helpers(fa):
     assert e.stride() == (1, 5, 35)
     a, b = fa.jl_randn((4, 3, 2), 1, device="cpu"), fa.jl_randn((4, 3, 2), 1, device="cpu")
     assert torch.equal(a, b)
+
+
+def test_circulant_sparse_matrices_match_reference_construction():
+    """circulant(N, M) / circulant(V) / batch_circulant (src/utils.jl:19-34): host-side index logic, no GPU.
+    Dense form against the definition: column j has V[w, j] at row first(cartesian_circulant((j-1)M + w))."""
+    import numpy as np
+    import torch
+    import fa_sm100a as fa
+    from oracle import fa_oracle as fo
+    N, M, B = 12, 5, 3
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal((M, N, B))
+    dense = fa.circulant(torch.from_numpy(V[:, :, 0])).to_dense().numpy()
+    want = np.zeros((N, N))
+    for j in range(1, N + 1):
+        for w in range(1, M + 1):
+            i, jj = fo.cartesian_circulant((j - 1) * M + w, N, M)
+            assert jj == j
+            want[i - 1, j - 1] = V[w - 1, j - 1, 0]
+    assert np.array_equal(dense, want)
+    ones = fa.circulant(N, M).to_dense().numpy()
+    assert np.array_equal(ones, (want != 0).astype(np.float64)) and ones.sum() == N * M
+    bd = fa.batch_circulant(torch.from_numpy(V)).to_dense().numpy()
+    for b in range(B):
+        blk = bd[b * N:(b + 1) * N, b * N:(b + 1) * N]
+        assert np.array_equal(blk, fa.circulant(torch.from_numpy(V[:, :, b])).to_dense().numpy())
+    assert np.count_nonzero(bd) == B * N * M

@@ -32,6 +32,24 @@ def timeit(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def graph_time(fn, reps):
+    """GPU-only time per call: `reps` calls captured into one CUDA graph and replayed (removes the Python
+    wrapper and launch latency from the small configs)."""
+    fn(); torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def rnd(shape, dtype):
     t = fa.jl_empty(shape, dtype)
     t.normal_()
@@ -86,6 +104,13 @@ def windowed(name, spatial, d, B, W, stride, pad, dtype, reps):
     report(name, "fwd", ms, 4.0 * WD * WD * d * L * B, nbytes, fa.last_path(), {"windows": L, "tokens_per_s": B * Ntok / ms * 1e3})
     ms = timeit(lambda: fa.windowed_fa_backward(q, k, v, g, l, m, W, stride, pad), max(1, reps // 3))
     report(name, "bwd", ms, 10.0 * WD * WD * d * L * B, 8 * Ntok * d * B * es + 8 * WD * L * B, fa.last_path())
+    try:   # GPU-only time (CUDA graph replay): what the kernels cost without the host wrapper
+        gf = graph_time(lambda: fa.windowed_fa(q, k, v, W, stride, pad), 20)
+        gb = graph_time(lambda: fa.windowed_fa_backward(q, k, v, g, l, m, W, stride, pad), 20)
+        report(name, "fwd_graph", gf, 4.0 * WD * WD * d * L * B, nbytes, fa.last_path())
+        report(name, "bwd_graph", gb, 10.0 * WD * WD * d * L * B, 8 * Ntok * d * B * es + 8 * WD * L * B, fa.last_path())
+    except Exception as e:
+        print(json.dumps({"config": name, "graph_error": repr(e)[:200]}), flush=True)
 
 
 def main():
