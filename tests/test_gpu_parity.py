@@ -176,6 +176,25 @@ def test_dense_bwd_tc_scale_invariance_and_bf16_internals():
         assert rel_err(to_np(x), x0, BF16) < 4e-3
 
 
+@pytest.mark.parametrize("dtype", [BF16, F16])
+def test_dense_bwd_tc_config3_geometry(dtype):
+    """BASELINE config 3 geometry (N = 8192, d = 128) at batch 1: every gradient entry against the blocked
+    float64 oracle (OneDFastBack) on the same (Q, K, V, O, dO, l, m); plus linearity in dO, a
+    size-independent property of the backward: grads(2 dO) == 2 grads(dO) up to the 16-bit rounding."""
+    N, d, B = 8192, 128, 1
+    q, k, v, g = (randn_np((N, d, B), s, dtype) for s in range(4))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.dense_fa(Q, K, V)
+    got = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    assert fa.last_path() == "tc"
+    want = fo.dense_fa_backward_blocked(*(t.astype(np.float64) for t in (q, k, v)), to_np(y), g.astype(np.float64), to_np(l), to_np(m))
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < 2e-3
+    got2 = fa.dense_fa_backward(Q, K, V, y, (G.float() * 2).to(dtype), l, m)
+    for a, a2 in zip(got, got2):
+        assert rel_err(to_np(a2), 2 * to_np(a), dtype, want_rounded=True) < 2e-3
+
+
 def test_dense_bwd_tc_matches_exact_simt_at_size():
     """Larger geometry (N=4096, d=128): the tcgen05 backward against this library's exact-fp32 SIMT
     backward on the same bf16 inputs (the SIMT path is itself pinned to the oracle above)."""
@@ -320,6 +339,38 @@ def test_windowed_bwd_tc(spatial, W, kws, d, dtype):
     if not (kws.get("stride", W) < W):          # no atomics when windows do not overlap: reproducible
         dq2, dk2, dv2 = fa.windowed_fa_backward(Q, K, V, G, l, m, W, **kws)
         assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dvv, dv2)
+
+
+def test_windowed_config5_geometry_tc():
+    """BASELINE config 5 geometry (64^3 volume, W = 5, stride 5, pad 3: 2744 exact-cover windows of 125
+    tokens, d = 64) at batch 1, bf16, forward and backward against the float64 oracle; plus the
+    size-independent property y(V = 1) == 1 on every position of an interior window (rows of P sum to 1,
+    count = 1; border windows hold zero-pad tokens whose v is 0, so their rows sum to less)."""
+    q, k, v, g = (randn_np((64, 64, 64, 64, 1), s, BF16) for s in range(4))
+    Q, K, V, G = (to_dev(t, BF16) for t in (q, k, v, g))
+    y, l, m = fa.windowed_fa(Q, K, V, 5, 5, 3)
+    assert fa.last_path() == "tc" and tuple(l.shape) == (125, 1, 2744, 1)
+    y0, l0, m0 = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), 5, 5, 3)
+    assert rel_err(to_np(y), y0, BF16) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+    got = fa.windowed_fa_backward(Q, K, V, G, l, m, 5, 5, 3)
+    want = fo.windowed_backward(*(t.astype(np.float64) for t in (q, k, v, g)), 5, 5, 3)
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, BF16) < 2e-3
+    ones = fa.jl_empty((64, 64, 64, 64, 1), BF16).fill_(1)
+    y1, _, _ = fa.windowed_fa(Q, K, ones, 5, 5, 3)
+    assert np.abs(to_np(y1)[2:62, 2:62, 2:62] - 1).max() < 2e-3
+    assert to_np(y1).max() < 1 + 2e-3 and to_np(y1).min() > 0
+
+
+def test_circulant_config4_geometry_tc():
+    """BASELINE config 4 geometry (N = 16384, periodic window 255, d = 64) at batch 1, bf16."""
+    N, d, W = 16384, 64, 255
+    Qn, Kn, Vn = (randn_np((N, d, 1), s, BF16) for s in range(3))
+    O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (Qn, Kn, Vn)), W)
+    O, l, m = fa.circulant_fa(*(to_dev(t, BF16) for t in (Qn, Kn, Vn)), W)
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(O), O0, BF16) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
 
 
 def test_windowed_fwd_config2_shape():
