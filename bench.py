@@ -287,7 +287,11 @@ def main():
     if rank == 0:
         peaks = measured_peaks()
         roof = {"bound": "tensor", "achieved": per_gpu, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": per_gpu / peaks["bf16_tflops"], "traffic": None,
+                "frac": per_gpu / peaks["bf16_tflops"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of one tc_fwd_kernel<128,bf16> launch at B = 512
+                # (ncu --set full, profiles/r1h_ncu_summary.md: 3.2226 GB + 1.0985 GB), scaled by the batch
+                "traffic": 4.3211e9 * Bn / 512.0, "traffic_unit": "bytes per launch (ncu, profiles/r1h_ncu_summary.md)",
+                "algorithmic_bytes_per_launch": (4.0 * N * D * 2 + 8.0 * N) * Bn,
                 "peak_source": peaks["source"] + " burst (cuBLAS bf16 GEMM)",
                 "frac_of_sustained": per_gpu / peaks["bf16_tflops_sustained"],
                 "frac_of_nominal_2250": per_gpu / 2250.0,
