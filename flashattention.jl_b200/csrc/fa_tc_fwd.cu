@@ -32,6 +32,7 @@
 // TMEM columns: S_t[b] at 128 t + 64 b (64 fp32 columns each), O_t at 256 + d t; P_t(j) aliases
 // the first 32 columns of S_t[j&1].
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "fa_common.cuh"
 #include "fa_ptx.cuh"
@@ -55,6 +56,13 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // lazy rescale: P may grow to 2^8 b
 #ifndef FA_PACKED
 #define FA_PACKED 1
 #endif
+// Clock traces (tools/trace_fwd.py, profiles/r1o_fwd_step_trace.md) show the softmax warps idle ~390 clk
+// per step between publishing P(j) and holding S(j+1) in registers (mbarrier wake-up + tcgen05.ld), although
+// S(j+1) is complete by the middle of the exp phase of step j: fetch it there, between the two 32-column
+// halves, when the barrier already flipped.
+#ifndef FA_PREFETCH_MID
+#define FA_PREFETCH_MID 1
+#endif
 #ifndef FA_EMU_PER_32
 #define FA_EMU_PER_32 0
 #endif
@@ -64,9 +72,13 @@ constexpr int EMU_PER_32 = FA_EMU_PER_32;   // exponentials per 32 emulated on t
 // tensor-bound dense configuration.  1: 256 threads, 256 TMEM columns and ~100 KB of smem, so TWO CTAs
 // share an SM and overlap each other's prologue (Q/K/V fetch latency) and epilogue (O store) -- the
 // short-loop circulant configuration, where a CTA lives for only (128 + W) / 64 key tiles.
-template <int D, int NQT = 2>
+// SPLIT = softmax threads per query row.  2: two warpgroups per Q tile, each thread owns 32 of the 64
+// columns of a step (row max exchanged through shared memory + a 64-thread named barrier, row sums kept
+// per thread): four softmax warps per scheduler instead of two hide the TMEM / MUFU / barrier latencies
+// of the serial softmax chain better.
+template <int D, int NQT = 2, int SPLIT = 1>
 struct Cfg {
-  static constexpr int THREADS = 128 + 128 * NQT;
+  static constexpr int THREADS = 128 + 128 * NQT * SPLIT;
   static constexpr int K_STAGES = (NQT == 1) ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 4);
   static constexpr int V_STAGES = (NQT == 1) ? ((D == 128) ? 3 : 6) : ((D == 128) ? 4 : 6);
   static constexpr int BOX_BYTES = 64 * D * 2;          // 64 tokens x D channels, 16-bit
@@ -87,7 +99,8 @@ struct Cfg {
   static constexpr int BAR_OFINAL = BAR_ODONE + 2;             // [2]  single use: all MMAs of tile t done
   static constexpr int NUM_BARS = BAR_OFINAL + 2;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
-  static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;   // + alignment slack
+  static constexpr int OFF_XCH = OFF_TMEM_SLOT + 16;             // SPLIT = 2: float[NQT][3][2][128] max / sum exchange
+  static constexpr int SMEM_BYTES = OFF_XCH + (SPLIT == 2 ? NQT * 3 * 2 * 128 * 4 : 0) + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = (NQT == 2) ? 512 : 256;
   static constexpr int COL_S = 0, COL_O = 128 * NQT;             // S_t[b] = 128 t + 64 b; O_t = COL_O + D t
   static constexpr int CTAS_PER_SM = (NQT == 2) ? 1 : 2;
@@ -100,7 +113,20 @@ struct TcParams {
   int N, B, W, p, mode;
   float scale_log2;      // tau * log2(e)
   int o_f32;             // store O as float32
+  int stagger;           // clocks by which the softmax warpgroup of Q tile 1 starts late (experiment)
+  long long* trace;      // FA_TRACE builds: CTA (0,0) records (clock) per (role, step, event); else NULL
 };
+
+#ifdef FA_TRACE
+// role: 0/1 = issuer of tile t, 2/3 = softmax warp 0 of tile t.  8 events per step, 64 steps.
+#define TRACE(role, step, ev)                                                                         \
+  do {                                                                                                \
+    if (prm.trace && blockIdx.x == 1 && blockIdx.y == 0 && lane == 0 && (step) >= 32 && (step) < 96)  \
+      prm.trace[((role) * 64 + ((step) - 32)) * 8 + (ev)] = clock64();                                 \
+  } while (0)
+#else
+#define TRACE(role, step, ev) do {} while (0)
+#endif
 
 __host__ __device__ inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -140,11 +166,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int D, int FMT, int NQT>
-__global__ void __launch_bounds__(Cfg<D, NQT>::THREADS, Cfg<D, NQT>::CTAS_PER_SM)
+template <int D, int FMT, int NQT, int SPLIT>
+__global__ void __launch_bounds__(Cfg<D, NQT, SPLIT>::THREADS, Cfg<D, NQT, SPLIT>::CTAS_PER_SM)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
               const __grid_constant__ CUtensorMap tmv, const TcParams prm) {
-  using C = Cfg<D, NQT>;
+  using C = Cfg<D, NQT, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase + C::OFF_Q, sK = sbase + C::OFF_K, sV = sbase + C::OFF_V;
@@ -163,7 +189,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     // K/V slots are released by every MMA issuer (count NQT)
     for (int i = 0; i < C::K_STAGES; ++i) { mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), NQT); }
     for (int i = 0; i < C::V_STAGES; ++i) { mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), NQT); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar(C::BAR_SFULL + i), 1); mbar_init(bar(C::BAR_PFULL + i), 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar(C::BAR_SFULL + i), 1); mbar_init(bar(C::BAR_PFULL + i), 128 * SPLIT); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(C::BAR_ODONE + i), 1); mbar_init(bar(C::BAR_OFINAL + i), 1); }
     fence_barrier_init();
   }
@@ -181,7 +207,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
   if (warp < 4) {
     // register pool of the CTA = THREADS x launch registers (168 for NQT = 2, 128 for NQT = 1):
     // 4 x 32 x 64 + 8 x 32 x 216 = 63488 <= 384 x 168;  4 x 32 x 56 + 4 x 32 x 200 = 32768 = 256 x 128
-    if (NQT == 2) setmaxnreg_dec<64>(); else setmaxnreg_dec<56>();
+    // SPLIT = 2: 640 x 96 launch registers:  4 x 32 x 56 + 16 x 32 x 104 = 60416 <= 61440
+    if (SPLIT == 2) setmaxnreg_dec<56>(); else if (NQT == 2) setmaxnreg_dec<64>(); else setmaxnreg_dec<56>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
 #pragma unroll
@@ -224,7 +251,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
         if (jp >= 0 && jp < nj) mbar_wait(bar(C::BAR_VFULL + jp % C::V_STAGES), (uint32_t)(jp / C::V_STAGES) & 1u);
         if (jp >= jlo && jp < jhi) {                                         // O_t += P_t(jp) V(jp)
           const int sv = jp % C::V_STAGES, i = jp - jlo, bb = i & 1;
+          TRACE(t, jp, 0);
           mbar_wait(bar(C::BAR_PFULL + 2 * t + bb), (uint32_t)(i >> 1) & 1u);
+          TRACE(t, jp, 1);
           tc_fence_after();
           const uint64_t vd = vdesc + (uint64_t)(sv * (C::BOX_BYTES >> 4));
           const uint32_t tP = tSt + 64 * bb;
@@ -236,7 +265,9 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           }
           __syncwarp();
         }
+        TRACE(t, g, 2);
         if (g < nj) mbar_wait(bar(C::BAR_KFULL + g % C::K_STAGES), (uint32_t)(g / C::K_STAGES) & 1u);
+        TRACE(t, g, 3);
         if (g >= jlo && g < jhi) {                                           // S_t[b] = Q_t K(g)^T
           const int sk = g % C::K_STAGES, i = g - jlo, bb = i & 1;
           if (i == 0) mbar_wait(bar(C::BAR_QFULL + t), 0);
@@ -250,6 +281,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             tc_commit(bar(C::BAR_SFULL + 2 * t + bb));
           }
           __syncwarp();
+          TRACE(t, g, 4);
         }
         // release the K/V slots of this step (every issuer arrives, whether or not it used them)
         if (elect_one()) {
@@ -260,6 +292,132 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       }
       if (elect_one()) tc_commit(bar(C::BAR_OFINAL + t));
       __syncwarp();
+    }
+  } else if (SPLIT == 2) {
+    // -------------------------------------------------------------- softmax, two threads per row
+    setmaxnreg_inc<104>();
+    const int sw = warp - 4, t = (sw >> 2) & 1, h = sw >> 3, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS0 = tmem_base + lane_addr + C::COL_S + 128 * t;
+    const uint32_t tO = tmem_base + lane_addr + C::COL_O + D * t;
+    const int qi = q0 + 128 * t + row;
+    const float scale = prm.scale_log2;
+    const int jlo = tr[t].jlo, jhi = tr[t].jhi;
+    const uint32_t xch = sbase + C::OFF_XCH + (uint32_t)(t * 3 * 2 * 128 * 4);      // [3][2 halves][128 rows]
+    const uint32_t nbar_id = 1u + (uint32_t)(t * 4 + quarter);                      // 64-thread named barrier of this row group
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(nbar_id) : "memory"); };
+    auto xst = [&](int slot, int hh, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(((slot * 2 + hh) * 128 + row) * 4)), "f"(v) : "memory"); };
+    auto xld = [&](int slot, int hh) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xch + (uint32_t)(((slot * 2 + hh) * 128 + row) * 4)) : "memory"); return v; };
+
+    if (jhi > jlo) {
+      float m_true = -INFINITY, m_used = -INFINITY;
+      const bool circ = prm.mode == MODE_CIRCULANT;
+      const int NN = prm.N, WW = prm.W, pp = prm.p;
+      float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
+      const float2 scale2 = make_float2(scale, scale);
+      uint32_t sc[32];
+      mbar_wait(bar(C::BAR_SFULL + 2 * t), 0);
+      tc_fence_after();
+      tmem_ld32(tS0 + 32 * h, sc);
+      tmem_wait_ld();
+      for (int j = jlo; j < jhi; ++j) {
+        const int i = j - jlo, bb = i & 1;
+        const uint32_t tS = tS0 + 64 * bb;
+        int lo = 0, hi = BN;
+        if (circ) { lo = (qi - pp) - (kbase + BN * j); hi = lo + WW; }
+        else { hi = NN - BN * j; }
+        if (lo > 32 * h || hi < 32 * h + 32) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = 32 * h + e;
+            if (col < lo || col >= hi) sc[e] = 0xff800000u;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3])));
+        }
+        const float mloc = fmaxf(mx0, mx1) * scale;
+        xst(i & 1, h, mloc);                      // the partner thread owns the other 32 columns of this row
+        pair_sync();
+        m_true = fmaxf(m_true, fmaxf(mloc, xld(i & 1, h ^ 1)));
+        const bool want = (m_true - m_used) > RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, want)) {      // identical in both warps of the pair: same rows, same m
+          const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_true);
+          if (i > 0) {
+            mbar_wait(bar(C::BAR_ODONE + t), (uint32_t)(i - 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = h * (D / 64); c < (h + 1) * (D / 64); ++c) {      // each thread rescales half the channels
+              uint32_t o[32];
+              tmem_ld32(tO + 32 * c, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tO + 32 * c, o);
+            }
+          }
+          l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
+          m_used = m_true;
+        }
+        const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+        const float2 negm2 = make_float2(neg_m, neg_m);
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])), scale2, negm2);
+          const float2 p = make_float2(ex2(x.x), ex2(x.y));
+          if (e & 2) l2b = __fadd2_rn(l2b, p); else l2a = __fadd2_rn(l2a, p);
+          pk[e >> 1] = pack2<FMT>(p.x, p.y);
+        }
+        tmem_st16(tS + 16 * h, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar(C::BAR_PFULL + 2 * t + bb));
+        if (j + 1 < jhi) {
+          mbar_wait(bar(C::BAR_SFULL + 2 * t + (bb ^ 1)), (uint32_t)((i + 1) >> 1) & 1u);
+          tc_fence_after();
+          tmem_ld32(tS0 + 64 * (bb ^ 1) + 32 * h, sc);
+          tmem_wait_ld();
+        }
+      }
+      const float l_half = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+      xst(2, h, l_half);
+      pair_sync();
+      const float l_run = l_half + xld(2, h ^ 1);
+
+      mbar_wait(bar(C::BAR_OFINAL + t), 0);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const bool in_range = qi < prm.N;
+#pragma unroll 1
+      for (int c = h * (D / 64); c < (h + 1) * (D / 64); ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + 32 * c, o);
+        tmem_wait_ld();
+        if (in_range) {
+          if (prm.o_f32) {
+            float* ob = static_cast<float*>(prm.o) + (size_t)b * D * prm.N + qi;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) ob[(size_t)(32 * c + e) * prm.N] = __uint_as_float(o[e]) * inv_l;
+          } else if (FMT == 1) {
+            __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(prm.o) + (size_t)b * D * prm.N + qi;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) ob[(size_t)(32 * c + e) * prm.N] = __float2bfloat16_rn(__uint_as_float(o[e]) * inv_l);
+          } else {
+            __half* ob = static_cast<__half*>(prm.o) + (size_t)b * D * prm.N + qi;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) ob[(size_t)(32 * c + e) * prm.N] = __float2half_rn(__uint_as_float(o[e]) * inv_l);
+          }
+        }
+      }
+      if (in_range && h == 0) {
+        prm.l[(size_t)b * prm.N + qi] = l_run * ex2(m_used - m_true);
+        prm.m[(size_t)b * prm.N + qi] = m_true * LN2;
+      }
     }
   } else {
     // -------------------------------------------------------------- softmax warpgroups
@@ -286,6 +444,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       auto softmax_step = [&](const int j, uint32_t (&sc)[2][32], uint32_t (&sn)[2][32]) {
         const int i = j - jlo, bb = i & 1;
         const uint32_t tS = tS0 + 64 * bb;
+        if ((warp & 3) == 0) TRACE(2 + t, j, 0);          // step start (S(j) already in registers)
         // opportunistic prefetch of S(j+1): taken now only if the tensor pipe already delivered it
         const bool more = j + 1 < jhi;
         const uint32_t nbar = bar(C::BAR_SFULL + 2 * t + (bb ^ 1)), npar = (uint32_t)((i + 1) >> 1) & 1u;
@@ -317,6 +476,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[1][e]), __uint_as_float(sc[1][e + 1])));
         }
         m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
+        if ((warp & 3) == 0) TRACE(2 + t, j, 1);          // max done
         // ---- lazy rescale of O and l (warp-uniform decision; this warp owns its 32 TMEM lanes)
         const bool want = (m_true - m_used) > RESCALE_THRESHOLD;   // inf on first use
         if (__any_sync(0xffffffffu, want)) {
@@ -378,20 +538,34 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             pk[e >> 1] = pack2<FMT>(p.x, p.y);
           }
           tmem_st16(tS + 16 * c, pk);
+          if (FA_PREFETCH_MID && c == 0 && more && !fetched && mbar_test_wait(nbar, npar)) {
+            tc_fence_after();
+            tmem_ld32(tS0 + 64 * (bb ^ 1), sn[0]);
+            tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);
+            fetched = true;
+          }
         }
+        if ((warp & 3) == 0) TRACE(2 + t, j, 2);          // exps + pack + st issued
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar(C::BAR_PFULL + 2 * t + bb));
+        if ((warp & 3) == 0) TRACE(2 + t, j, 3);          // P published
         if (more && !fetched) {                // late path: S(j+1) was not ready before the exp phase
           mbar_wait(nbar, npar);
+          if ((warp & 3) == 0) TRACE(2 + t, j, 4);        // S(j+1) available
           tc_fence_after();
           tmem_ld32(tS0 + 64 * (bb ^ 1), sn[0]);
           tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);
         }
         tmem_wait_ld();                        // S(j+1) registers are valid from here on
+        if ((warp & 3) == 0) TRACE(2 + t, j, 5);          // S(j+1) in registers
       };
 
       uint32_t sA[2][32], sB[2][32];
+      if (t == 1 && prm.stagger > 0) {           // de-phase the two warpgroups: see launch_tc
+        const long long t0 = clock64();
+        while (clock64() - t0 < prm.stagger) {}
+      }
       mbar_wait(bar(C::BAR_SFULL + 2 * t), 0);
       tc_fence_after();
       tmem_ld32(tS0, sA[0]);
@@ -493,7 +667,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int dtype, long long N, int D, 
   return FA_OK;
 }
 
-template <int D, int FMT, int NQT>
+template <int D, int FMT, int NQT, int SPLIT = 1>
 int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   CUtensorMap tmq, tmk, tmv;
   int rc;
@@ -505,8 +679,14 @@ int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.N = (int)g.N; prm.B = (int)g.B; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
   prm.scale_log2 = g.tau * LOG2E;
   prm.o_f32 = a.o_f32;
-  using C = Cfg<D, NQT>;
-  auto kern = tc_fwd_kernel<D, FMT, NQT>;
+  static const int stagger = [] { const char* e = getenv("FA_FWD_STAGGER"); return e ? atoi(e) : 0; }();
+  prm.stagger = stagger;
+  prm.trace = nullptr;
+#ifdef FA_TRACE
+  { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
+  using C = Cfg<D, NQT, SPLIT>;
+  auto kern = tc_fwd_kernel<D, FMT, NQT, SPLIT>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const dim3 grid((unsigned)((g.N + 128 * NQT - 1) / (128 * NQT)), (unsigned)g.B);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
@@ -542,6 +722,8 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
     if (g.d == 128) return fmt ? launch_tc<128, 1, 1>(g, a, dtype, st) : launch_tc<128, 0, 1>(g, a, dtype, st);
     return fmt ? launch_tc<64, 1, 1>(g, a, dtype, st) : launch_tc<64, 0, 1>(g, a, dtype, st);
   }
+  static const int split = [] { const char* e = getenv("FA_FWD_SPLIT"); return e ? atoi(e) : 1; }();
+  if (split == 2 && g.d == 128) return fmt ? launch_tc<128, 1, 2, 2>(g, a, dtype, st) : launch_tc<128, 0, 2, 2>(g, a, dtype, st);
   if (g.d == 128) return fmt ? launch_tc<128, 1, 2>(g, a, dtype, st) : launch_tc<128, 0, 2>(g, a, dtype, st);
   return fmt ? launch_tc<64, 1, 2>(g, a, dtype, st) : launch_tc<64, 0, 2>(g, a, dtype, st);
 }
