@@ -78,7 +78,10 @@ constexpr int EMU_PER_32 = FA_EMU_PER_32;   // exponentials per 32 emulated on t
 // of the serial softmax chain better.
 template <int D, int NQT = 2, int SPLIT = 1>
 struct Cfg {
-  static constexpr int THREADS = 128 + 128 * NQT * SPLIT;
+  // SPLIT == 3: one softmax warpgroup per Q tile plus one HELPER warpgroup per Q tile that computes the
+  // row maxima of S(j+1) off the softmax warps' serial chain (and publishes them through shared memory)
+  static constexpr bool HELP = (SPLIT == 3);
+  static constexpr int THREADS = 128 + 128 * NQT * (HELP ? 2 : SPLIT);
   static constexpr int K_STAGES = (NQT == 1) ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 4);
   static constexpr int V_STAGES = (NQT == 1) ? ((D == 128) ? 3 : 6) : ((D == 128) ? 4 : 6);
   static constexpr int BOX_BYTES = 64 * D * 2;          // 64 tokens x D channels, 16-bit
@@ -97,10 +100,11 @@ struct Cfg {
   static constexpr int BAR_PFULL = BAR_SFULL + 4;              // [2][2]
   static constexpr int BAR_ODONE = BAR_PFULL + 4;              // [2]  one completion per PV_t
   static constexpr int BAR_OFINAL = BAR_ODONE + 2;             // [2]  single use: all MMAs of tile t done
-  static constexpr int NUM_BARS = BAR_OFINAL + 2;
+  static constexpr int BAR_MAX = BAR_OFINAL + 2;               // [2][2] HELP: row maxima of S_t[b] published
+  static constexpr int NUM_BARS = BAR_MAX + 4;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int OFF_XCH = OFF_TMEM_SLOT + 16;             // SPLIT = 2: float[NQT][3][2][128] max / sum exchange
-  static constexpr int SMEM_BYTES = OFF_XCH + (SPLIT == 2 ? NQT * 3 * 2 * 128 * 4 : 0) + 1024;   // + alignment slack
+  static constexpr int SMEM_BYTES = OFF_XCH + (SPLIT >= 2 ? NQT * 3 * 2 * 128 * 4 : 0) + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = (NQT == 2) ? 512 : 256;
   static constexpr int COL_S = 0, COL_O = 128 * NQT;             // S_t[b] = 128 t + 64 b; O_t = COL_O + D t
   static constexpr int CTAS_PER_SM = (NQT == 2) ? 1 : 2;
@@ -189,7 +193,11 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     // K/V slots are released by every MMA issuer (count NQT)
     for (int i = 0; i < C::K_STAGES; ++i) { mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), NQT); }
     for (int i = 0; i < C::V_STAGES; ++i) { mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), NQT); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar(C::BAR_SFULL + i), 1); mbar_init(bar(C::BAR_PFULL + i), 128 * SPLIT); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(C::BAR_SFULL + i), 1);
+      mbar_init(bar(C::BAR_PFULL + i), SPLIT == 2 ? 256 : 128);
+      mbar_init(bar(C::BAR_MAX + i), 128);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(C::BAR_ODONE + i), 1); mbar_init(bar(C::BAR_OFINAL + i), 1); }
     fence_barrier_init();
   }
@@ -208,7 +216,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     // register pool of the CTA = THREADS x launch registers (168 for NQT = 2, 128 for NQT = 1):
     // 4 x 32 x 64 + 8 x 32 x 216 = 63488 <= 384 x 168;  4 x 32 x 56 + 4 x 32 x 200 = 32768 = 256 x 128
     // SPLIT = 2: 640 x 96 launch registers:  4 x 32 x 56 + 16 x 32 x 104 = 60416 <= 61440
-    if (SPLIT == 2) setmaxnreg_dec<56>(); else if (NQT == 2) setmaxnreg_dec<64>(); else setmaxnreg_dec<56>();
+    // HELP: 4 x 32 x 56 + 8 x 32 x 64 (helpers) + 8 x 32 x 144 (softmax) = 60416 <= 640 x 96
+    if (SPLIT >= 2) setmaxnreg_dec<56>(); else if (NQT == 2) setmaxnreg_dec<64>(); else setmaxnreg_dec<56>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
 #pragma unroll
@@ -292,6 +301,48 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       }
       if (elect_one()) tc_commit(bar(C::BAR_OFINAL + t));
       __syncwarp();
+    }
+  } else if (C::HELP && warp >= 4 + 4 * NQT) {
+    // -------------------------------------------------------------- helper warpgroups: row max of S(j)
+    setmaxnreg_dec<64>();
+    const int t = (warp - 4 - 4 * NQT) >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS0 = tmem_base + lane_addr + C::COL_S + 128 * t;
+    const int qi = q0 + 128 * t + row;
+    const int jlo = tr[t].jlo, jhi = tr[t].jhi;
+    const bool circ = prm.mode == MODE_CIRCULANT;
+    const uint32_t hm = sbase + C::OFF_XCH + (uint32_t)(t * 2 * 128 * 4);      // float[2 buffers][128 rows]
+    for (int j = jlo; j < jhi; ++j) {
+      const int i = j - jlo, bb = i & 1;
+      mbar_wait(bar(C::BAR_SFULL + 2 * t + bb), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      int lo = 0, hi = BN;
+      if (circ) { lo = (qi - prm.p) - (kbase + BN * j); hi = lo + prm.W; }
+      else { hi = prm.N - BN * j; }
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(tS0 + 64 * bb + 32 * c, sv);
+        tmem_wait_ld();
+        float m0 = -INFINITY, m1 = -INFINITY;
+        if (lo > 32 * c || hi < 32 * c + 32) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = 32 * c + e;
+            if (col < lo || col >= hi) sv[e] = 0xff800000u;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+        }
+        mx = fmaxf(mx, fmaxf(m0, m1));
+      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(hm + (uint32_t)((bb * 128 + row) * 4)), "f"(mx) : "memory");
+      mbar_arrive(bar(C::BAR_MAX + 2 * t + bb));      // release: the store above is visible to whoever sees the phase
     }
   } else if (SPLIT == 2) {
     // -------------------------------------------------------------- softmax, two threads per row
@@ -421,7 +472,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     }
   } else {
     // -------------------------------------------------------------- softmax warpgroups
-    if (NQT == 2) setmaxnreg_inc<216>(); else setmaxnreg_inc<200>();
+    if (C::HELP) setmaxnreg_inc<144>(); else if (NQT == 2) setmaxnreg_inc<216>(); else setmaxnreg_inc<200>();
     const int t = (warp - 4) >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
@@ -469,13 +520,21 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             }
         }
         // ---- running max (thread-local: one thread owns one row)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (C::HELP) {
+          // the helper warpgroup of this tile has already reduced S(j) (it saw s_full long before we got here)
+          mbar_wait(bar(C::BAR_MAX + 2 * t + bb), (uint32_t)(i >> 1) & 1u);
+          float hmx;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(hmx) : "r"(sbase + C::OFF_XCH + (uint32_t)(((t * 2 + bb) * 128 + row) * 4)) : "memory");
+          m_true = fmaxf(m_true, hmx * scale);
+        } else {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[0][e]), __uint_as_float(sc[0][e + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[1][e]), __uint_as_float(sc[1][e + 1])));
+          for (int e = 0; e < 32; e += 2) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[0][e]), __uint_as_float(sc[0][e + 1])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[1][e]), __uint_as_float(sc[1][e + 1])));
+          }
+          m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
         }
-        m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
         if ((warp & 3) == 0) TRACE(2 + t, j, 1);          // max done
         // ---- lazy rescale of O and l (warp-uniform decision; this warp owns its 32 TMEM lanes)
         const bool want = (m_true - m_used) > RESCALE_THRESHOLD;   // inf on first use
@@ -724,6 +783,7 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   }
   static const int split = [] { const char* e = getenv("FA_FWD_SPLIT"); return e ? atoi(e) : 1; }();
   if (split == 2 && g.d == 128) return fmt ? launch_tc<128, 1, 2, 2>(g, a, dtype, st) : launch_tc<128, 0, 2, 2>(g, a, dtype, st);
+  if (split == 3 && g.d == 128) return fmt ? launch_tc<128, 1, 2, 3>(g, a, dtype, st) : launch_tc<128, 0, 2, 3>(g, a, dtype, st);
   if (g.d == 128) return fmt ? launch_tc<128, 1, 2>(g, a, dtype, st) : launch_tc<128, 0, 2>(g, a, dtype, st);
   return fmt ? launch_tc<64, 1, 2>(g, a, dtype, st) : launch_tc<64, 0, 2>(g, a, dtype, st);
 }
