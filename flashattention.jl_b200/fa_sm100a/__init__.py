@@ -32,7 +32,7 @@ __all__ = [
     "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
-    "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys", "circulant", "batch_circulant",
+    "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys", "circulant2d_keys", "circulant", "batch_circulant",
     "dense_dpa", "windowed_dpa", "block_dpa", "circulant_dpa", "shard_batch", "ring_dense_fa", "ring_dense_fa_backward",
 ]
 
@@ -71,6 +71,10 @@ def _load():
         "fa_circulant_fwd": (ci, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, ci, ci, vp]),
         "fa_workspace_bytes_circulant_bwd": (sz, [i64, i64, i64, i64, i64, ci, ci]),
         "fa_circulant_bwd": (ci, [vp] * 10 + [i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
+        "fa_circulant2d_index": (ci, [i64, i64, i64, pi64]),
+        "fa_circulant2d_fwd": (ci, [vp] * 6 + [i64, i64, i64, i64, i64, i64, ci, ci, vp]),
+        "fa_workspace_bytes_circulant2d_bwd": (sz, [i64, i64, i64]),
+        "fa_circulant2d_bwd": (ci, [vp] * 10 + [i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
         "fa_workspace_bytes_windowed_fwd": (sz, [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci]),
         "fa_windowed_fwd": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
         "fa_workspace_bytes_windowed_bwd": (sz, [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci]),
@@ -103,7 +107,8 @@ EXPORTED_SYMBOLS = (
     "fa_workspace_bytes_circulant_bwd fa_circulant_bwd fa_workspace_bytes_windowed_fwd fa_windowed_fwd "
     "fa_workspace_bytes_windowed_bwd fa_windowed_bwd fa_window fa_unwindow fa_softmax fa_dense_fwd_host "
     "fa_circulant_fwd_host fa_windowed_fwd_host fa_release_host_staging fa_shard_batch fa_merge_partials "
-    "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd").split()
+    "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd "
+    "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd").split()
 
 
 def _check(rc: int, what: str):
@@ -478,8 +483,14 @@ def circulant_fa_(O, l, m, Q, K, V, W: int, flags: int = 0):
     """``circulant_fa!(O, l, m, Q, K, V, W) -> (O, l, m)`` (src/circulant.jl:9-118), 1-D periodic band."""
     _same(Q, K, V)
     Q, K, V = (jl_array(t) for t in (Q, K, V))
+    if Q.ndim == 4:                       # 2-D periodic neighbourhood (the reference's todo, README.md:38-41,53)
+        X, Y, d, B = (int(s) for s in Q.shape)
+        with torch.cuda.device(Q.device):
+            _check(lib.fa_circulant2d_fwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(l), _ptr(m), X, Y, d, int(V.shape[2]), B, int(W),
+                                          _dt(Q), flags, _stream(Q)), "fa_circulant2d_fwd")
+        return O, l, m
     if Q.ndim != 3:
-        raise FaError("circulant_fa! is 1-D only: Q, K, V must be (N, d, B) (README.md:38-41)")
+        raise FaError("circulant_fa!: Q, K, V must be (N, d, B) or (X, Y, d, B)")
     N, d, B = (int(s) for s in Q.shape)
     dv = int(V.shape[1])
     if Q.is_cuda:
@@ -495,6 +506,12 @@ def circulant_fa_(O, l, m, Q, K, V, W: int, flags: int = 0):
 def circulant_fa(Q, K, V, W: int, flags: int = 0):
     """``circulant_fa(Q, K, V, W)``: allocating wrapper.  The reference's drops ``W``
     (src/circulant.jl:6, SURVEY B-1); this one passes it."""
+    if Q.ndim == 4:
+        X, Y, d, B = (int(s) for s in Q.shape)
+        O = jl_empty((X, Y, int(V.shape[2]), B), Q.dtype, Q.device)
+        l = jl_empty((X * Y, 1, B), torch.float32, Q.device)
+        m = jl_empty((X * Y, 1, B), torch.float32, Q.device)
+        return circulant_fa_(O, l, m, Q, K, V, W, flags)
     N, d, B = (int(s) for s in Q.shape)
     O = jl_empty((N, int(V.shape[1]), B), Q.dtype, Q.device)
     l = jl_empty((N, 1, B), torch.float32, Q.device)
@@ -507,6 +524,15 @@ def circulant_fa_backward(Q, K, V, O, dO, l, m, W: int, flags: int = 0):
     _same(Q, K, V, O, dO)
     Q, K, V, O, dO = (jl_array(t) for t in (Q, K, V, O, dO))
     l, m = (jl_array(t, torch.float32) for t in (l, m))
+    if Q.ndim == 4:
+        X, Y, d, B = (int(s) for s in Q.shape)
+        dQ, dK, dV = (jl_empty(t.shape, t.dtype, t.device) for t in (Q, K, V))
+        ws = _workspace(lib.fa_workspace_bytes_circulant2d_bwd(X, Y, B), Q.device)
+        with torch.cuda.device(Q.device):
+            _check(lib.fa_circulant2d_bwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m), _ptr(dQ), _ptr(dK), _ptr(dV),
+                                          X, Y, d, int(V.shape[2]), B, int(W), _dt(Q), flags, _ptr(ws), ws.numel(), _stream(Q)),
+                   "fa_circulant2d_bwd")
+        return dQ, dK, dV
     N, d, B = (int(s) for s in Q.shape)
     dv = int(V.shape[1])
     dQ, dK, dV = (jl_empty(t.shape, t.dtype, t.device) for t in (Q, K, V))
@@ -523,6 +549,14 @@ def cartesian_circulant(n: int, N: int, M: int):
     keys = circulant_keys(N, M)
     j = -(-n // M)
     return int(keys[(n - 1) % M, j - 1]) + 1, j
+
+
+def circulant2d_keys(X: int, Y: int, W: int) -> torch.Tensor:
+    """Key set of the 2-D circulant attention as a 0-based int64 ``(W*W, X*Y)`` tensor (column = query
+    ``y*X + x``, row = ``t*W + s``)."""
+    buf = (ctypes.c_int64 * (X * Y * W * W))()
+    _check(lib.fa_circulant2d_index(X, Y, W, buf), "fa_circulant2d_index")
+    return torch.tensor(list(buf), dtype=torch.int64).reshape(X * Y, W * W).permute(1, 0)
 
 
 def circulant_keys(N: int, W: int) -> torch.Tensor:

@@ -50,3 +50,38 @@ function circulant_fa_backward(Q::CuArray{T, 3}, K::CuArray{T, 3}, V::CuArray{T,
     check(rc, "fa_circulant_bwd")
     return dQ, dK, dV
 end
+
+# ---- 2-D circulant (periodic neighbourhood) attention: the reference's todo (README.md:38-41,53).
+# Q, K, V :: (X, Y, d, B); keys of query (x, y): (mod(x-p+s, X), mod(y-p+t, Y)), s, t = 0..W-1.
+function circulant_fa(Q::CuArray{T, 4}, K::CuArray{T, 4}, V::CuArray{T, 4}, W::Int; flags::Integer=0) where {T}
+    X, Y, d, batchsize = size(Q)
+    dv = size(V, 3)
+    O = similar(Q, X, Y, dv, batchsize)
+    l = statarray(Q, X * Y, 1, batchsize)
+    m = statarray(Q, X * Y, 1, batchsize)
+    rc = ccall(sym(:fa_circulant2d_fwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}),
+               devptr(Q), devptr(K), devptr(V), devptr(O), devptr(l), devptr(m),
+               X, Y, d, dv, batchsize, W, fa_dtype(T), Cint(flags), current_stream())
+    check(rc, "fa_circulant2d_fwd")
+    return O, l, m
+end
+
+function circulant_fa_backward(Q::CuArray{T, 4}, K::CuArray{T, 4}, V::CuArray{T, 4}, O::CuArray{T, 4}, dO::CuArray{T, 4},
+                               l::CuArray{Float32, 3}, m::CuArray{Float32, 3}, W::Int; flags::Integer=0) where {T}
+    X, Y, d, batchsize = size(Q)
+    dv = size(V, 3)
+    dQ, dK, dV = similar(Q), similar(K), similar(V)
+    nws = ccall(sym(:fa_workspace_bytes_circulant2d_bwd), Csize_t, (Int64, Int64, Int64), X, Y, batchsize)
+    ws = CuArray{UInt8}(undef, max(nws, 256))
+    rc = ccall(sym(:fa_circulant2d_bwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint,
+                Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+               devptr(Q), devptr(K), devptr(V), devptr(O), devptr(dO), devptr(l), devptr(m),
+               devptr(dQ), devptr(dK), devptr(dV), X, Y, d, dv, batchsize, W, fa_dtype(T), Cint(flags),
+               devptr(ws), length(ws), current_stream())
+    check(rc, "fa_circulant2d_bwd")
+    return dQ, dK, dV
+end

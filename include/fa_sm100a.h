@@ -99,6 +99,20 @@ int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o,
                      int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- 2-D circulant (periodic neighbourhood) attention: the reference's stated todo (README.md:38-41,53),
+ *      the direct product of the 1-D definition.  q,k,v,o :: (X, Y, d|dv, B); l,m :: (X*Y, 1, B);
+ *      keys of query (x,y): (mod(x-p+s, X), mod(y-p+t, Y)), s,t = 0..W-1, p = (W-1)/2; W <= min(X,Y), W <= 16.
+ *      Exact fp32 math for every dtype (parity-first implementation). */
+int fa_circulant2d_index(int64_t X, int64_t Y, int64_t W, int64_t* keys);   /* keys[(y*X+x)*W*W + t*W + s] */
+int fa_circulant2d_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                       int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W,
+                       int dtype, int flags, void* stream);
+size_t fa_workspace_bytes_circulant2d_bwd(int64_t X, int64_t Y, int64_t B);
+int fa_circulant2d_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                       const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                       int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- windowed: replaces windowed_fa / block_fa (src/windowed.jl:1-23) with window/unwindow
  *      (src/utils.jl:36-54) fused in.  q,k,v,y :: (dims[0..ndim), d|dv, B); l,m :: (W^D,1,L,B). */
 size_t fa_workspace_bytes_windowed_fwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,

@@ -468,6 +468,60 @@ def circulant_backward(Q, K, V, dO, W: int):
     return _F(dQ), _F(dK), _F(dV)
 
 
+def circulant2d_keys(X: int, Y: int, W: int):
+    """Keys of the 2-D circulant attention (the reference's todo, README.md:38-41,53): direct product of the
+    1-D key set mod(j-1-p+t, N)+1 (src/utils.jl:6-17).  0-based (W*W, X*Y): row t*W+s, column y*X+x."""
+    p = (W - 1) // 2
+    x = np.arange(X)[None, None, None, :]
+    y = np.arange(Y)[None, None, :, None]
+    s = np.arange(W)[None, :, None, None]
+    t = np.arange(W)[:, None, None, None]
+    xx = np.mod(x - p + s, X)
+    yy = np.mod(y - p + t, Y)
+    return (yy * X + xx).reshape(W * W, X * Y)
+
+
+def circulant2d_fa(Q, K, V, W: int):
+    """2-D circulant attention on (X, Y, d, B) arrays -> (O (X,Y,dv,B), l, m (X*Y,1,B))."""
+    Q, K, V = _F(Q), _F(K), _F(V)
+    X, Y, d, B = Q.shape
+    dv = V.shape[2]
+    if W > X or W > Y:
+        raise ValueError("W must not exceed the spatial extents")
+    q, k, v = (t.reshape(X * Y, t.shape[2], B, order="F") for t in (Q, K, V))
+    keys = circulant2d_keys(X, Y, W)
+    tau = Q.dtype.type(1) / Q.dtype.type(math.sqrt(d))
+    S = np.einsum("ikb,wikb->wib", q, k[keys]) * tau
+    m = S.max(axis=0, keepdims=True)
+    P = np.exp(S - m)
+    l = P.sum(axis=0, keepdims=True)
+    O = np.einsum("wib,wicb->icb", P / l, v[keys])
+    return _F(O.reshape(X, Y, dv, B, order="F")), _F(l.reshape(X * Y, 1, B)), _F(m.reshape(X * Y, 1, B))
+
+
+def circulant2d_backward(Q, K, V, dO, W: int):
+    """Backward of circulant2d_fa (A.5.1 restricted to the periodic neighbourhood)."""
+    Q, K, V, dO = _F(Q), _F(K), _F(V), _F(dO)
+    X, Y, d, B = Q.shape
+    dv = V.shape[2]
+    q, k, v, g = (t.reshape(X * Y, t.shape[2], B, order="F") for t in (Q, K, V, dO))
+    keys = circulant2d_keys(X, Y, W)
+    tau = Q.dtype.type(1) / Q.dtype.type(math.sqrt(d))
+    S = np.einsum("ikb,wikb->wib", q, k[keys]) * tau
+    P = np.exp(S - S.max(axis=0, keepdims=True))
+    P = P / P.sum(axis=0, keepdims=True)
+    dP = np.einsum("icb,wicb->wib", g, v[keys])
+    dS = P * (dP - (P * dP).sum(axis=0, keepdims=True))
+    dq = np.einsum("wib,wikb->ikb", dS, k[keys]) * tau
+    dk = np.zeros_like(k)
+    dvv = np.zeros_like(v)
+    flat = keys.reshape(-1)
+    np.add.at(dk, flat, (dS[:, :, None, :] * q[None, :, :, :]).reshape(-1, d, B) * tau)
+    np.add.at(dvv, flat, (P[:, :, None, :] * g[None, :, :, :]).reshape(-1, dv, B))
+    rs = lambda t, c: _F(t.reshape(X, Y, c, B, order="F"))
+    return rs(dq, d), rs(dk, d), rs(dvv, dv)
+
+
 def circulant_backward_given(Q, K, V, O, dO, l, m, W: int):
     """Band-restricted ``OneDFastBack`` (src_cpp/FlashAttention.cpp:238-246) on the
     SAVED forward results: ``P = exp(tau q.k - m) / l`` and ``D = rowsum(dO o O)`` use the

@@ -120,3 +120,15 @@ def test_circulant_sparse_matrices_match_reference_construction():
         blk = bd[b * N:(b + 1) * N, b * N:(b + 1) * N]
         assert np.array_equal(blk, fa.circulant(torch.from_numpy(V[:, :, b])).to_dense().numpy())
     assert np.count_nonzero(bd) == B * N * M
+
+
+def test_circulant2d_index_bit_exact():
+    import numpy as np
+    import fa_sm100a as fa
+    from oracle import fa_oracle as fo
+    for X, Y, W in ((6, 7, 3), (8, 8, 8), (5, 9, 4), (16, 3, 1)):
+        got = fa.circulant2d_keys(X, Y, W).numpy()
+        assert np.array_equal(got, fo.circulant2d_keys(X, Y, W))
+    import pytest
+    with pytest.raises(fa.FaError):
+        fa.circulant2d_keys(4, 8, 5)          # W > X would duplicate keys

@@ -486,3 +486,27 @@ def test_autograd_wrappers_match_oracle_gradients(dtype):
     want = fo.circulant_backward(*(t.astype(np.float64) for t in (q, k, v, g)), 33)
     for got, w in zip((Q.grad, K.grad, V.grad), want):
         assert rel_err(to_np(got), w, dtype) < max(tol, 3e-3 if dtype == BF16 else 0)
+
+
+# ------------------------------------------------------------------------------- 2-D circulant
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("X,Y,d,B,W", [(8, 8, 16, 2, 3), (20, 12, 64, 2, 7), (9, 5, 8, 1, 5), (16, 16, 32, 2, 4), (33, 17, 64, 1, 1)])
+def test_circulant2d_fwd_bwd(X, Y, d, B, W, dtype):
+    q, k, v, g = (randn_np((X, Y, d, B), s, dtype) for s in range(4))
+    O0, l0, m0 = fo.circulant2d_fa(*(t.astype(np.float64) for t in (q, k, v)), W)
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    O, l, m = fa.circulant_fa(Q, K, V, W)
+    tol = 1e-5 if dtype == F32 else 1e-4          # exact fp32 math; 16-bit only in the storage
+    assert tuple(O.shape) == O0.shape and tuple(l.shape) == l0.shape
+    assert rel_err(to_np(O), O0, dtype) < tol and rel_err(to_np(l), l0) < 1e-5 and rel_err(to_np(m), m0) < 1e-5
+    want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
+    got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
+    btol = 1e-5 if dtype == F32 else 3e-3          # D = rowsum(dO o O) from the bf16-stored O
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < btol
+
+
+def test_circulant2d_rejects_bad_window():
+    q = fa.jl_randn((6, 8, 4, 1), 0)
+    with pytest.raises(fa.FaError):
+        fa.circulant_fa(q, q, q, 7)

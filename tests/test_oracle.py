@@ -300,3 +300,25 @@ def test_backward_given_forward_results_equals_recomputed():
     b = fo.dense_backward(Q, K, V, G)
     for x, y in zip(a, b):
         assert np.abs(x - y).max() < 1e-12
+
+
+def test_circulant2d_oracle_definition():
+    """2-D circulant attention (reference todo, README.md:38-41,53): with W == X == Y every key is used once,
+    so it must equal dense attention; its backward against central finite differences."""
+    rng = np.random.default_rng(5)
+    Q, K, V = (np.asfortranarray(rng.standard_normal((5, 5, 4, 2))) for _ in range(3))
+    O, l, m = fo.circulant2d_fa(Q, K, V, 5)
+    y, l2, m2 = fo.dense_fa(Q, K, V)
+    assert np.abs(O - y).max() < 1e-12 and np.abs(l.reshape(-1) - l2.reshape(-1)).max() < 1e-12
+    keys = fo.circulant2d_keys(6, 7, 3)
+    assert keys.shape == (9, 42) and keys[4, 0] == 0 and sorted(keys[:, 0]) == sorted([0, 1, 5, 6, 7, 11, 36, 37, 41])
+    Q, K, V, G = (np.asfortranarray(rng.standard_normal((6, 7, 3, 1))) for _ in range(4))
+    grads = fo.circulant2d_backward(Q, K, V, G, 3)
+    f = lambda q, k, v: (fo.circulant2d_fa(q, k, v, 3)[0] * G).sum()
+    eps = 1e-6
+    for which, gr in enumerate(grads):
+        for idx in ((2, 3, 1, 0), (0, 0, 0, 0), (5, 6, 2, 0)):
+            args_p, args_m = [Q.copy(), K.copy(), V.copy()], [Q.copy(), K.copy(), V.copy()]
+            args_p[which][idx] += eps
+            args_m[which][idx] -= eps
+            assert abs((f(*args_p) - f(*args_m)) / (2 * eps) - gr[idx]) < 1e-7
