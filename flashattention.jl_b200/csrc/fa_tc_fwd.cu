@@ -63,6 +63,9 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // lazy rescale: P may grow to 2^8 b
 #ifndef FA_PREFETCH_MID
 #define FA_PREFETCH_MID 1
 #endif
+#ifndef FA_EXP_SWP
+#define FA_EXP_SWP 0
+#endif
 #ifndef FA_EXP_BLOCK
 #define FA_EXP_BLOCK 8      // elements per exp block (0 = pairwise loop); 8: +1.5 % over pairwise, same-box A/B
 #endif
@@ -576,7 +579,26 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
-#if FA_EXP_BLOCK
+#if FA_EXP_SWP
+          // software pipeline: the ex2 pair of column pair u is issued FA_EXP_SWP pairs before its sum / pack,
+          // interleaved with them (MUFU accepts one warp instruction per 8 clk: the 7 slots in between are
+          // filled with the packed-math instructions of older pairs instead of stalling on the pipe)
+          {
+            float2 pb[FA_EXP_SWP];
+#pragma unroll
+            for (int u = 0; u < 16 + FA_EXP_SWP; ++u) {
+              if (u >= FA_EXP_SWP) {
+                const int w = u - FA_EXP_SWP;
+                if (w & 1) l2b = __fadd2_rn(l2b, pb[w % FA_EXP_SWP]); else l2a = __fadd2_rn(l2a, pb[w % FA_EXP_SWP]);
+                pk[w] = pack2<FMT>(pb[w % FA_EXP_SWP].x, pb[w % FA_EXP_SWP].y);
+              }
+              if (u < 16) {
+                const float2 x = __ffma2_rn(make_float2(__uint_as_float(sc[c][2 * u]), __uint_as_float(sc[c][2 * u + 1])), scale2, negm2);
+                pb[u % FA_EXP_SWP] = make_float2(ex2(x.x), ex2(x.y));
+              }
+            }
+          }
+#elif FA_EXP_BLOCK
           // blocks of 8: all eight ex2 are issued before the first result is consumed, so the sum / pack
           // instructions never wait on a MUFU that was issued two instructions earlier
 #pragma unroll
