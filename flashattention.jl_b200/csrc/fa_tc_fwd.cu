@@ -63,6 +63,9 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // lazy rescale: P may grow to 2^8 b
 #ifndef FA_PREFETCH_MID
 #define FA_PREFETCH_MID 1
 #endif
+#ifndef FA_EMU_PAIRS
+#define FA_EMU_PAIRS 0      // column pairs per exp block whose exponentials are evaluated on the FMA pipe
+#endif
 #ifndef FA_EXP_SWP
 #define FA_EXP_SWP 0
 #endif
@@ -608,7 +611,25 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             for (int u = 0; u < FA_EXP_BLOCK / 2; ++u)
               x[u] = __ffma2_rn(make_float2(__uint_as_float(sc[c][e0 + 2 * u]), __uint_as_float(sc[c][e0 + 2 * u + 1])), scale2, negm2);
 #pragma unroll
-            for (int u = 0; u < FA_EXP_BLOCK / 2; ++u) { p[u].x = ex2(x[u].x); p[u].y = ex2(x[u].y); }
+            for (int u = 0; u < FA_EXP_BLOCK / 2; ++u) {
+              if (u >= FA_EXP_BLOCK / 2 - FA_EMU_PAIRS) {
+                // this pair on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error 9e-5,
+                // far below the 16-bit rounding of P): fills issue slots the MUFU pipe leaves idle
+                float2 xx = x[u];
+                xx.x = fmaxf(xx.x, -126.f); xx.y = fmaxf(xx.y, -126.f);
+                const float2 xf = __fadd2_rd(xx, make_float2(12582912.f, 12582912.f));
+                const float2 xr = __fadd2_rn(xf, make_float2(-12582912.f, -12582912.f));
+                const float2 fr = __fadd2_rn(xx, make_float2(-xr.x, -xr.y));
+                float2 qq = __ffma2_rn(fr, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                                       make_float2(0.227564394474029541f, 0.227564394474029541f));
+                qq = __ffma2_rn(qq, fr, make_float2(0.695146143436431885f, 0.695146143436431885f));
+                qq = __ffma2_rn(qq, fr, make_float2(1.f, 1.f));
+                p[u].x = __uint_as_float(__float_as_uint(qq.x) + (__float_as_uint(xf.x) << 23));
+                p[u].y = __uint_as_float(__float_as_uint(qq.y) + (__float_as_uint(xf.y) << 23));
+              } else {
+                p[u].x = ex2(x[u].x); p[u].y = ex2(x[u].y);
+              }
+            }
 #pragma unroll
             for (int u = 0; u < FA_EXP_BLOCK / 2; ++u) {
               if (u & 1) l2b = __fadd2_rn(l2b, p[u]); else l2a = __fadd2_rn(l2a, p[u]);
