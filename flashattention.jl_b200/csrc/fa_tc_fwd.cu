@@ -110,7 +110,8 @@ struct Cfg {
   static constexpr int BAR_ODONE = BAR_PFULL + 4;              // [2]  one completion per PV_t
   static constexpr int BAR_OFINAL = BAR_ODONE + 2;             // [2]  single use: all MMAs of tile t done
   static constexpr int BAR_MAX = BAR_OFINAL + 2;               // [2][2] HELP: row maxima of S_t[b] published
-  static constexpr int NUM_BARS = BAR_MAX + 4;
+  static constexpr int BAR_MXX = BAR_MAX + 4;                  // [2 tiles][4 quarters][2 halves][2 parities] SPLIT = 2
+  static constexpr int NUM_BARS = BAR_MXX + (SPLIT == 2 ? 32 : 0);
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int OFF_XCH = OFF_TMEM_SLOT + 16;             // SPLIT = 2: float[NQT][3][2][128] max / sum exchange
   static constexpr int SMEM_BYTES = OFF_XCH + (SPLIT >= 2 ? NQT * 3 * 2 * 128 * 4 : 0) + 1024;   // + alignment slack
@@ -208,6 +209,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       mbar_init(bar(C::BAR_PFULL + i), SPLIT == 2 ? 256 : 128);
       mbar_init(bar(C::BAR_MAX + i), 128);
     }
+    if (SPLIT == 2) for (int i = 0; i < 32; ++i) mbar_init(bar(C::BAR_MXX + i), 32);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(C::BAR_ODONE + i), 1); mbar_init(bar(C::BAR_OFINAL + i), 1); }
     fence_barrier_init();
   }
@@ -355,7 +357,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       mbar_arrive(bar(C::BAR_MAX + 2 * t + bb));      // release: the store above is visible to whoever sees the phase
     }
   } else if (SPLIT == 2) {
-    // -------------------------------------------------------------- softmax, two threads per row
+    // -------------------------------------------------------------- softmax, two threads per row (v2)
+    // A lone warp's exp phase is the sum of its dispatch intervals (profiles/r1o_fwd_step_trace.md), so the
+    // 64 columns of a step are split over two threads (two warps of the same lane quarter).  The row max of
+    // S(j+1) is exchanged EARLY: each thread reduces its half right after fetching it at the end of step j
+    // and publishes it through shared memory + an mbarrier, so the partner's value is there when step j+1
+    // starts and no named barrier sits in the chain.
     setmaxnreg_inc<104>();
     const int sw = warp - 4, t = (sw >> 2) & 1, h = sw >> 3, quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -365,26 +372,21 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
     const int qi = q0 + 128 * t + row;
     const float scale = prm.scale_log2;
     const int jlo = tr[t].jlo, jhi = tr[t].jhi;
-    const uint32_t xch = sbase + C::OFF_XCH + (uint32_t)(t * 3 * 2 * 128 * 4);      // [3][2 halves][128 rows]
-    const uint32_t nbar_id = 1u + (uint32_t)(t * 4 + quarter);                      // 64-thread named barrier of this row group
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(nbar_id) : "memory"); };
-    auto xst = [&](int slot, int hh, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch + (uint32_t)(((slot * 2 + hh) * 128 + row) * 4)), "f"(v) : "memory"); };
-    auto xld = [&](int slot, int hh) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xch + (uint32_t)(((slot * 2 + hh) * 128 + row) * 4)) : "memory"); return v; };
+    const uint32_t xch = sbase + C::OFF_XCH + (uint32_t)(t * 3 * 2 * 128 * 4);      // float [3 slots][2 halves][128 rows]
+    auto xaddr = [&](int slot, int hh) { return xch + (uint32_t)(((slot * 2 + hh) * 128 + row) * 4); };
+    auto xst = [&](int slot, int hh, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(xaddr(slot, hh)), "f"(v) : "memory"); };
+    auto xld = [&](int slot, int hh) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(xaddr(slot, hh)) : "memory"); return v; };
+    // max-exchange barriers: [tile][quarter][half][step parity], 32 arrivals each
+    auto mxbar = [&](int hh, int par) { return bar(C::BAR_MXX + ((t * 4 + quarter) * 2 + hh) * 2 + par); };
+    const bool circ = prm.mode == MODE_CIRCULANT;
+    const int NN = prm.N, WW = prm.W, pp = prm.p;
 
     if (jhi > jlo) {
       float m_true = -INFINITY, m_used = -INFINITY;
-      const bool circ = prm.mode == MODE_CIRCULANT;
-      const int NN = prm.N, WW = prm.W, pp = prm.p;
       float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
       const float2 scale2 = make_float2(scale, scale);
-      uint32_t sc[32];
-      mbar_wait(bar(C::BAR_SFULL + 2 * t), 0);
-      tc_fence_after();
-      tmem_ld32(tS0 + 32 * h, sc);
-      tmem_wait_ld();
-      for (int j = jlo; j < jhi; ++j) {
-        const int i = j - jlo, bb = i & 1;
-        const uint32_t tS = tS0 + 64 * bb;
+      // mask + local max of one fetched half-row, published for the partner
+      auto reduce_publish = [&](uint32_t (&sv)[32], int j) -> float {
         int lo = 0, hi = BN;
         if (circ) { lo = (qi - pp) - (kbase + BN * j); hi = lo + WW; }
         else { hi = NN - BN * j; }
@@ -392,18 +394,35 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int col = 32 * h + e;
-            if (col < lo || col >= hi) sc[e] = 0xff800000u;
+            if (col < lo || col >= hi) sv[e] = 0xff800000u;
           }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3])));
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
         }
-        const float mloc = fmaxf(mx0, mx1) * scale;
-        xst(i & 1, h, mloc);                      // the partner thread owns the other 32 columns of this row
-        pair_sync();
+        const float ml = fmaxf(mx0, mx1) * scale;
+        const int i = j - jlo;
+        xst(i & 1, h, ml);
+        mbar_arrive(mxbar(h, i & 1));          // release: the store is visible to whoever observes the phase
+        return ml;
+      };
+      uint32_t sc[32], sn[32];
+      mbar_wait(bar(C::BAR_SFULL + 2 * t), 0);
+      tc_fence_after();
+      tmem_ld32(tS0 + 32 * h, sc);
+      tmem_wait_ld();
+      float mloc = reduce_publish(sc, jlo);
+
+      auto step = [&](const int j, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+        const int i = j - jlo, bb = i & 1;
+        const uint32_t tS = tS0 + 64 * bb;
+        const bool more = j + 1 < jhi;
+        const uint32_t nbar = bar(C::BAR_SFULL + 2 * t + (bb ^ 1)), npar = (uint32_t)((i + 1) >> 1) & 1u;
+        // partner's half of the row max (published at the end of its previous step)
+        mbar_wait(mxbar(h ^ 1, i & 1), (uint32_t)(i >> 1) & 1u);
         m_true = fmaxf(m_true, fmaxf(mloc, xld(i & 1, h ^ 1)));
         const bool want = (m_true - m_used) > RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, want)) {      // identical in both warps of the pair: same rows, same m
@@ -427,27 +446,47 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
         const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
         const float2 negm2 = make_float2(neg_m, neg_m);
         uint32_t pk[16];
+        bool fetched = false;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])), scale2, negm2);
-          const float2 p = make_float2(ex2(x.x), ex2(x.y));
-          if (e & 2) l2b = __fadd2_rn(l2b, p); else l2a = __fadd2_rn(l2a, p);
-          pk[e >> 1] = pack2<FMT>(p.x, p.y);
+        for (int e0 = 0; e0 < 32; e0 += 8) {
+          float2 x[4], p[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            x[u] = __ffma2_rn(make_float2(__uint_as_float(cur[e0 + 2 * u]), __uint_as_float(cur[e0 + 2 * u + 1])), scale2, negm2);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { p[u].x = ex2(x[u].x); p[u].y = ex2(x[u].y); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (u & 1) l2b = __fadd2_rn(l2b, p[u]); else l2a = __fadd2_rn(l2a, p[u]);
+            pk[(e0 >> 1) + u] = pack2<FMT>(p[u].x, p[u].y);
+          }
+          if (e0 == 8 && more && mbar_test_wait(nbar, npar)) {      // S(j+1) usually complete by now
+            tc_fence_after();
+            tmem_ld32(tS0 + 64 * (bb ^ 1) + 32 * h, nxt);
+            fetched = true;
+          }
         }
         tmem_st16(tS + 16 * h, pk);
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar(C::BAR_PFULL + 2 * t + bb));
-        if (j + 1 < jhi) {
-          mbar_wait(bar(C::BAR_SFULL + 2 * t + (bb ^ 1)), (uint32_t)((i + 1) >> 1) & 1u);
-          tc_fence_after();
-          tmem_ld32(tS0 + 64 * (bb ^ 1) + 32 * h, sc);
+        if (more) {
+          if (!fetched) {
+            mbar_wait(nbar, npar);
+            tc_fence_after();
+            tmem_ld32(tS0 + 64 * (bb ^ 1) + 32 * h, nxt);
+          }
           tmem_wait_ld();
+          mloc = reduce_publish(nxt, j + 1);
         }
+      };
+      for (int j = jlo; j < jhi; j += 2) {
+        step(j, sc, sn);
+        if (j + 1 < jhi) step(j + 1, sn, sc);
       }
       const float l_half = (l2a.x + l2a.y) + (l2b.x + l2b.y);
       xst(2, h, l_half);
-      pair_sync();
+      asm volatile("bar.sync %0, 64;" ::"r"(1u + (uint32_t)(t * 4 + quarter)) : "memory");
       const float l_run = l_half + xld(2, h ^ 1);
 
       mbar_wait(bar(C::BAR_OFINAL + t), 0);
