@@ -570,6 +570,19 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
               if (col < lo || col >= hi) sc[c][e] = 0xff800000u;   // -inf
             }
         }
+        // A 64-key tile that lies outside the band of EVERY row of this warp (circulant: the CTA's key range
+        // covers 128 + W - 1 keys, a warp's rows only 32 + W - 1) contributes P = 0: skip max, rescale and the
+        // 64 exponentials, publish zeros.  One warp-uniform branch per step.
+        // (Only in the one-Q-tile instantiation the band kernels use: in the NQT = 2 kernel the extra branch costs
+        // the dense path 4 %, measured.)
+        const bool allmasked = NQT == 1 && __all_sync(0xffffffffu, hi <= 0 || lo >= BN);
+        if (allmasked) {
+          uint32_t z[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) z[e] = 0u;
+          tmem_st16(tS, z);
+          tmem_st16(tS + 16, z);
+        } else {
         // ---- running max (thread-local: one thread owns one row)
         if (C::HELP) {
           // the helper warpgroup of this tile has already reduced S(j) (it saw s_full long before we got here)
@@ -713,6 +726,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);
             fetched = true;
           }
+        }
         }
         if (pp_on) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (t ^ 1)) : "memory");
         if ((warp & 3) == 0) TRACE(2 + t, j, 2);          // exps + pack + st issued
