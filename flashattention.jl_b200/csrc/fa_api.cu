@@ -30,6 +30,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
              int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st);
 int tmem_bw_probe(int mode, int nwarps, int iters, long long* out_dev, cudaStream_t st);
+int umma_rate_probe(int mode, int n_cols, int iters, int blocks, long long* out_dev, cudaStream_t st);
 
 namespace {
 
@@ -507,6 +508,14 @@ int fa_debug_tmem_bw(int mode, int nwarps, int iters, long long* out_dev, void* 
   if (rc) return rc;
   if ((nwarps != 1 && nwarps != 4 && nwarps != 8) || iters <= 0 || !out_dev) { set_error("bad probe arguments"); return FA_ERR_INVALID; }
   return tmem_bw_probe(mode, nwarps, iters, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// tcgen05.mma throughput by operand source and N (see fa_tc_probe.cu).  Not a product API.
+int fa_debug_umma_rate(int mode, int n_cols, int iters, int blocks, long long* out_dev, void* stream) {
+  int rc = need_device();
+  if (rc) return rc;
+  if (mode < 0 || mode > 7 || n_cols < 16 || n_cols > 256 || n_cols % 16 || iters <= 0 || blocks <= 0 || !out_dev) { set_error("bad probe arguments"); return FA_ERR_INVALID; }
+  return umma_rate_probe(mode, n_cols, iters, blocks, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

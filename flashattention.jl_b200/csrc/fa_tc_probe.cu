@@ -147,7 +147,63 @@ __global__ void tmem_bw_kernel(int mode, int iters, long long* out) {
   __syncthreads();
   if (warp == 0) tmem_dealloc(slot, 512);
 }
+// UMMA issue-rate / operand-bandwidth probe: `iters` rounds of 8 kind::f16 MMAs (M = 128, K = 16 each, one
+// 128-channel K loop) with N = n_cols, A from shared memory (mode 0, MN-major SW128) or from TMEM (mode 1),
+// B from shared memory (MN-major SW128).  Data is whatever the buffers hold; only the clocks matter.
+__global__ void umma_rate_kernel(int mode, int n_cols, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = sbase, sB = sbase + 32768, bars = sbase + 32768 + 65536, slot = bars + 16;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bars, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  for (int i = threadIdx.x; i < (32768 + 65536) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_raw + (sbase - smem_u32(smem_raw)))[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+  if (warp == 1) {
+    // mode bit 0: A from TMEM; bit 1: A K-major in smem; bit 2: B K-major in smem (else MN-major)
+    const bool a_tmem = mode & 1, a_km = mode & 2, b_km = mode & 4;
+    const uint32_t idesc = make_idesc_f16(0, 0, (a_tmem || a_km) ? 0 : 1, b_km ? 0 : 1, 128, n_cols);
+    const uint64_t ad = a_km ? make_smem_desc_sw128(sA, 16, 1024) : make_smem_desc_sw128(sA, 16384, 1024);
+    const uint64_t bd = b_km ? make_smem_desc_sw128(sB, 16, 1024) : make_smem_desc_sw128(sB, 16384, 1024);
+    // K-major: 64 K-elements per 128-byte row -> k-steps 0..3 advance 32 B inside a tile, 4..7 sit in the next tile
+    auto a_off = [&](int ks) { return a_km ? (uint64_t)((ks >> 2) * (16384 >> 4) + (ks & 3) * 2) : (uint64_t)(ks * 128); };
+    auto b_off = [&](int ks) { return b_km ? (uint64_t)((ks >> 2) * (32768 >> 4) + (ks & 3) * 2) : (uint64_t)(ks * 128); };
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (a_tmem) mma_ts(tmem_base, tmem_base + 256 + ks * 8, bd + b_off(ks), idesc, ks > 0 ? 1u : 0u);
+          else mma_ss(tmem_base, ad + a_off(ks), bd + b_off(ks), idesc, ks > 0 ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit(bars);
+    __syncwarp();
+    mbar_wait(bars, 0);
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
 }  // namespace
+
+int umma_rate_probe(int mode, int n_cols, int iters, int blocks, long long* out_dev, cudaStream_t st) {
+  const int smem = 32768 + 65536 + 64 + 1024;
+  FA_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<blocks, 64, smem, st>>>(mode, n_cols, iters, out_dev);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
 
 int tmem_bw_probe(int mode, int nwarps, int iters, long long* out_dev, cudaStream_t st) {
   tmem_bw_kernel<<<1, 32 * nwarps, 0, st>>>(mode, iters, out_dev);
