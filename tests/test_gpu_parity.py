@@ -510,3 +510,42 @@ def test_circulant2d_rejects_bad_window():
     q = fa.jl_randn((6, 8, 4, 1), 0)
     with pytest.raises(fa.FaError):
         fa.circulant_fa(q, q, q, 7)
+
+
+# ------------------------------------------------------------------------------- edge cases on the tcgen05 paths
+@pytest.mark.parametrize("dtype", [BF16, F16])
+def test_tc_edge_shapes(dtype):
+    """Smallest / degenerate geometries the tcgen05 kernels accept: N = 8 (one partial tile), a band of one key
+    (W = 1: O = V), a band that is the whole ring (W = N), windows with gaps (stride > W: uncovered
+    positions are NaN forward and receive zero gradient), windows of one token."""
+    # dense, N = 8
+    q, k, v, g = (randn_np((8, 64, 2), s, dtype) for s in range(4))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.dense_fa(Q, K, V)
+    assert fa.last_path() == "tc"
+    y0, l0, m0 = fo.dense_fa(*(t.astype(np.float64) for t in (q, k, v)))
+    assert rel_err(to_np(y), y0, dtype) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+    got = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    want = fo.dense_fa_backward_blocked(*(t.astype(np.float64) for t in (q, k, v)), to_np(y), g.astype(np.float64), to_np(l), to_np(m))
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < 2e-3
+    # circulant, W = 1 (each query sees only itself -> O = V, l = 1) and W = N (dense)
+    q, k, v = (randn_np((128, 64, 1), s, dtype) for s in range(3))
+    Q, K, V = (to_dev(t, dtype) for t in (q, k, v))
+    O, l, m = fa.circulant_fa(Q, K, V, 1)
+    assert fa.last_path() == "tc" and torch.equal(O, V) and np.abs(to_np(l) - 1).max() < 1e-6
+    O, l, m = fa.circulant_fa(Q, K, V, 128)
+    yd, ld, md = fo.dense_fa(*(t.astype(np.float64) for t in (q, k, v)))
+    assert rel_err(to_np(O), yd, dtype) < 2e-3 and rel_err(to_np(l) * np.exp(to_np(m) - md), ld) < 2e-3
+    # windowed with gaps (stride 6 > W 4) and single-token windows (W = 1)
+    for spatial, W, kws in (((26,), 4, dict(stride=6, pad=0)), ((10, 6), 1, dict(stride=1, pad=0))):
+        q, k, v, g = (randn_np(spatial + (64, 2), s, dtype) for s in range(4))
+        Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+        y, l, m = fa.windowed_fa(Q, K, V, W, **kws)
+        assert fa.last_path() == "tc"
+        y0, l0, m0 = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), W, **kws)
+        assert rel_err(to_np(y), y0, dtype) < 2e-3          # NaN pattern included
+        got = fa.windowed_fa_backward(Q, K, V, G, l, m, W, **kws)
+        want = fo.windowed_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W, **kws)
+        for a, b_ in zip(got, want):
+            assert rel_err(to_np(a), b_, dtype) < 2e-3
