@@ -31,6 +31,8 @@ int tc_probe(int mode, const void* a, const void* b, const float* p, float* out,
              int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st);
 int tmem_bw_probe(int mode, int nwarps, int iters, long long* out_dev, cudaStream_t st);
 int umma_rate_probe(int mode, int n_cols, int iters, int blocks, long long* out_dev, cudaStream_t st);
+int tma5d_probe(const void* base, const long long* dims, const long long* strides_bytes, const int* box, const int* coord,
+                unsigned char* out_dev, cudaStream_t st);
 
 namespace {
 
@@ -516,6 +518,14 @@ int fa_debug_umma_rate(int mode, int n_cols, int iters, int blocks, long long* o
   if (rc) return rc;
   if (mode < 0 || mode > 7 || n_cols < 16 || n_cols > 256 || n_cols % 16 || iters <= 0 || blocks <= 0 || !out_dev) { set_error("bad probe arguments"); return FA_ERR_INVALID; }
   return umma_rate_probe(mode, n_cols, iters, blocks, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+// One 5-D TMA box load (bf16 elements) copied back out (see fa_tc_probe.cu).  Not a product API.
+int fa_debug_tma5d(const void* base, const long long* dims, const long long* strides_bytes, const int* box, const int* coord,
+                   unsigned char* out_dev, void* stream) {
+  int rc = need_device();
+  if (rc) return rc;
+  return tma5d_probe(base, dims, strides_bytes, box, coord, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

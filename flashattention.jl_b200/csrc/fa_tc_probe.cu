@@ -195,7 +195,48 @@ __global__ void umma_rate_kernel(int mode, int n_cols, int iters, long long* out
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
+// 5-D TMA tile-mode probe: one box load at (c0..c4) into shared memory, copied out to `out` (bytes).
+__global__ void tma5d_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, int c2, int c3, int c4,
+                                   unsigned bytes, unsigned char* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar = sbase + 60 * 1024;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, bytes);
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(sbase), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  }
+  mbar_wait(bar, 0);
+  for (unsigned i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = sp[i];
+}
 }  // namespace
+
+int tma5d_probe(const void* base, const long long* dims, const long long* strides_bytes, const int* box, const int* coord,
+                unsigned char* out_dev, cudaStream_t st) {
+  typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) { set_error("no encode fn"); return FA_ERR_CUDA; }
+  CUtensorMap tm;
+  cuuint64_t d[5], sb[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  unsigned bytes = 2;
+  for (int i = 0; i < 5; ++i) { d[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; bytes *= (unsigned)box[i]; }
+  for (int i = 0; i < 4; ++i) sb[i] = (cuuint64_t)strides_bytes[i];
+  CUresult r = reinterpret_cast<Fn>(p)(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), d, sb, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("encode failed %d", (int)r); return FA_ERR_CUDA; }
+  const int smem = 62 * 1024 + 1024;
+  FA_CUDA_TRY(cudaFuncSetAttribute(tma5d_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tma5d_probe_kernel<<<1, 128, smem, st>>>(tm, coord[0], coord[1], coord[2], coord[3], coord[4], bytes, out_dev);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
 
 int umma_rate_probe(int mode, int n_cols, int iters, int blocks, long long* out_dev, cudaStream_t st) {
   const int smem = 32768 + 65536 + 64 + 1024;

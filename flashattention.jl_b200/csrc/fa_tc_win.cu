@@ -20,6 +20,9 @@
 //     divides by the count, src/windowed.jl:16-19).
 // HBM-bound by design: q/k/v are read once per covering window, y written once.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
 #include "fa_common.cuh"
 #include "fa_ptx.cuh"
 
@@ -102,12 +105,21 @@ struct WinParams {
   float scale_log2;
 };
 
-template <int D, int NT> struct WCfg {
+// TMAG: the gather is done by TMA instead of per-thread loads (exact-cover windows, stride == W): one 5-D box
+// (x: all windows of the CTA, y: W, z: W, all channels, 1 batch) per tensor lands in a staging buffer --
+// full sectors, zero fill outside the volume = the zero padding of `window`, no registers, no load
+// instructions, and the box of the next tensor / next group is in flight while the CTA works -- and is then
+// repacked shared -> shared into the SWIZZLE_128B [channel][token] operand tiles.
+template <int D, int NT, int TMAG = 0> struct WCfg {
   static constexpr int THREADS = 128 * NT;
   static constexpr int BOX_BYTES = 64 * D * 2;
   static constexpr int TILE_BYTES = 2 * BOX_BYTES;
   static constexpr int OFF_TILES = 0;                        // [NT][q,k,v]
-  static constexpr int OFF_SRC = NT * 3 * TILE_BYTES;        // long long[MAXE]
+  static constexpr int STG_BYTES = TMAG ? 40 * 1024 : 0;     // one staged box (all or a slice of the channels of one tensor)
+  static constexpr int OFF_STG = NT * 3 * TILE_BYTES;        // [2] staging buffers
+  static constexpr int RPK_MAX = 1024;                       // repack table entries (run groups x tokens per run group)
+  static constexpr int OFF_RPK = OFF_STG + 2 * STG_BYTES;    // uint2[RPK_MAX]
+  static constexpr int OFF_SRC = OFF_RPK + (TMAG ? RPK_MAX * 8 : 0);   // long long[MAXE]
   static constexpr int OFF_ROW = OFF_SRC + MAXE * 8;         // int[MAXE]
   static constexpr int OFF_WIN = OFF_ROW + MAXE * 4;         // int4[256] window origins
   static constexpr int OFF_BAR = OFF_WIN + 256 * 16;
@@ -118,17 +130,35 @@ template <int D, int NT> struct WCfg {
   // 228 KB of shared memory per SM, 1 KB of it reserved per resident CTA
   static constexpr int BY_SMEM = 228 * 1024 / (SMEM_BYTES + 1024);
   static constexpr int CTAS_PER_SM = 512 / TMEM_COLS < BY_SMEM ? 512 / TMEM_COLS : BY_SMEM;
-  static_assert(NT != 2 || D != 64 || CTAS_PER_SM == 2, "d = 64 pair kernel must fit twice per SM");
+  static_assert(TMAG || NT != 2 || D != 64 || CTAS_PER_SM == 2, "d = 64 pair kernel must fit twice per SM");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
+
+struct TmaGeo {       // TMAG only
+  int BX, by, bz;     // box extents (tokens) in x, y, z
+  int RGN, TW;        // run groups per window (W^(D-1)), tokens per run group of the CTA (nwc * W)
+  int gpr;            // groups per window row = ceil(Lx / nwc)
+  int CH, ncs;        // channels per box, boxes per tensor (CH * ncs = d)
+  unsigned box_bytes;
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 
 // ---- table: entry e = warp-item * 32 + lane  ->  (source element offset | -1, (tile << 8) | row | -1)
 // wininfo[win] = {x0, y0, z0, batch | -1}: origin (first token per dim, may be negative = padding) of
 // every window of this CTA iteration, computed once per window; entries then need 32-bit math only.
-__device__ __forceinline__ void build_wininfo(const Geo& g, const WinMap& mp, long long gw0, long long nwin, int4* wininfo, int tid) {
+__device__ __forceinline__ void build_wininfo(const Geo& g, const WinMap& mp, long long gw0, long long nwin, int4* wininfo, int tid,
+                                              int nvalid = 1 << 30) {
   if (tid < mp.nwc) {
     const long long gw = gw0 + tid;
     int4 wi4 = make_int4(0, 0, 0, -1);
-    if (gw < nwin) {
+    if (gw < nwin && tid < nvalid) {
       const long long b = gw / g.L;
       int w = (int)(gw - b * g.L);
       int o3[3];
@@ -177,10 +207,11 @@ __device__ __forceinline__ void build_table(const Geo& g, const WinMap& mp, cons
   }
 }
 
-template <int D, int NT, int FMT>
-__global__ void __launch_bounds__(WCfg<D, NT>::THREADS, WCfg<D, NT>::CTAS_PER_SM)
-tc_win_fwd_kernel(const WinParams prm) {
-  using C = WCfg<D, NT>;
+template <int D, int NT, int FMT, int TMAG>
+__global__ void __launch_bounds__(WCfg<D, NT, TMAG>::THREADS, WCfg<D, NT, TMAG>::CTAS_PER_SM)
+tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                  const __grid_constant__ CUtensorMap tmv, const WinParams prm, const TmaGeo tg) {
+  using C = WCfg<D, NT, TMAG>;
   using T = typename El<FMT>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -188,15 +219,30 @@ tc_win_fwd_kernel(const WinParams prm) {
   long long* tsrc = reinterpret_cast<long long*>(sptr + C::OFF_SRC);
   int* trow = reinterpret_cast<int*>(sptr + C::OFF_ROW);
   int4* wininfo = reinterpret_cast<int4*>(sptr + C::OFF_WIN);
-  const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16;
+  const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16, bar_stg = bar_s + 24;   // bar_stg[2]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NWARPS = C::THREADS / 32;
   const Geo& g = prm.g;
   const WinMap mp = prm.mp;
   const long long N = g.N;
   const int WD = g.WD;
+  uint2* rpk = reinterpret_cast<uint2*>(sptr + C::OFF_RPK);
 
-  if (tid == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_barrier_init(); }
+  if (tid == 0) {
+    mbar_init(bar_s, 1); mbar_init(bar_o, 1); mbar_init(bar_stg, 1); mbar_init(bar_stg + 8, 1); fence_barrier_init();
+    if (TMAG) { prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv); }
+  }
+  if (TMAG) {
+    // static repack table: entry (run group rg, token t of the CTA's x-range) -> operand-tile position
+    for (int e = tid; e < tg.RGN * tg.TW; e += C::THREADS) {
+      const int rg = e / tg.TW, t = e - rg * tg.TW;
+      const int w = t / g.W, kx = t - w * g.W;
+      const int til = w / mp.G, rr = (w - til * mp.G) * WD + rg * g.W + kx;
+      const uint32_t dst_lo = (uint32_t)(til * 3 * C::TILE_BYTES + (rr >> 6) * C::BOX_BYTES + (rr & 7) * 2);
+      rpk[e] = make_uint2(dst_lo | ((uint32_t)((rr & 63) >> 3) << 24), (uint32_t)(rg * tg.BX + t) | ((uint32_t)w << 16));
+    }
+    for (int e = tg.RGN * tg.TW + tid; e < (tg.RGN * tg.TW + 255) / 256 * 256; e += C::THREADS) rpk[e] = make_uint2(0u, 0xffff0000u);
+  }
   if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
   // rows no window maps to (>= G * W^D) stay zero for the whole kernel: K/V pad rows must be finite
   for (int i = tid; i < NT * 3 * C::TILE_BYTES / 16; i += C::THREADS)
@@ -219,14 +265,87 @@ tc_win_fwd_kernel(const WinParams prm) {
   constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);
   const float2 scale2 = make_float2(prm.scale_log2, prm.scale_log2);
 
+  // TMAG: a group is nwc x-adjacent windows of ONE window row; decode (first window, valid count, box origin)
+  auto decode = [&](long long grp, long long& gw0, int& nvalid, int& x0, int& y0, int& z0, int& b) {
+    const long long rowi = grp / tg.gpr;
+    const int gi = (int)(grp - rowi * tg.gpr);
+    const int wx0 = gi * mp.nwc;
+    nvalid = g.o[0] - wx0 < mp.nwc ? g.o[0] - wx0 : mp.nwc;
+    const int wy = (int)(rowi % g.o[1]);
+    const long long r2 = rowi / g.o[1];
+    const int wz = (int)(r2 % g.o[2]);
+    b = (int)(r2 / g.o[2]);
+    gw0 = (((long long)b * g.o[2] + wz) * g.o[1] + wy) * g.o[0] + wx0;
+    x0 = wx0 * g.stride - g.pad;                      // the box itself starts at the 16-byte boundary below x0
+    y0 = g.nd >= 2 ? wy * g.stride - g.pad : 0;
+    z0 = g.nd >= 3 ? wz * g.stride - g.pad : 0;
+  };
+  // load number `pos` of this CTA (lpg = 3 * ncs per group: q, k, v in channel slices) goes to staging buffer pos & 1.
+  // TMA wants the innermost coordinate 16-byte aligned: the box starts at the multiple of 8 below x0.
+  const int lpg = 3 * tg.ncs;
+  auto issue_load = [&](long long grp, int j, uint32_t pos) {
+    long long gw0; int nvalid, x0, y0, z0, b;
+    decode(grp, gw0, nvalid, x0, y0, z0, b);
+    const int x = j / tg.ncs, cs = j - x * tg.ncs;
+    const uint32_t bar = bar_stg + 8u * (pos & 1u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of the buffer precede this async write
+    mbar_arrive_expect_tx(bar, tg.box_bytes);
+    tma_load_5d(sbase + C::OFF_STG + (pos & 1u) * C::STG_BYTES, x == 0 ? &tmq : x == 1 ? &tmk : &tmv, bar,
+                (x0 + 1024) / 8 * 8 - 1024, y0, z0, cs * tg.CH, b);
+  };
+  if (TMAG && tid == 0 && (long long)blockIdx.x < prm.ngroups) { issue_load(blockIdx.x, 0, 0); issue_load(blockIdx.x, 1, 1); }
+
   uint32_t it = 0;
   for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x, ++it) {
-    const long long gw0 = grp * mp.nwc;
-    build_wininfo(g, mp, gw0, prm.nwin, wininfo, tid);
+    long long gw0 = grp * mp.nwc;
+    int nvalid = mp.nwc, xshift = 0;
+    if (TMAG) { int x0, y0, z0, b; decode(grp, gw0, nvalid, x0, y0, z0, b); xshift = (x0 + 1024) & 7; }
+    build_wininfo(g, mp, gw0, prm.nwin, wininfo, tid, nvalid);
     __syncthreads();
     build_table(g, mp, wininfo, D, tsrc, trow, tid, C::THREADS);
     __syncthreads();
 
+    if (TMAG) {
+      // ---- gather by TMA + shared -> shared repack (8 table entries per lane held in registers per pass)
+      const int nent = tg.RGN * tg.TW;
+      const uint32_t cstride = (uint32_t)(tg.RGN * tg.BX * 2);
+#pragma unroll 1
+      for (int j = 0; j < lpg; ++j) {
+        const uint32_t pos = (uint32_t)lpg * it + (uint32_t)j;
+        const int x = j / tg.ncs, cs = j - x * tg.ncs;
+        mbar_wait(bar_stg + 8u * (pos & 1u), (pos >> 1) & 1u);
+        const uint32_t stg = sbase + C::OFF_STG + (pos & 1u) * C::STG_BYTES + (uint32_t)xshift * 2u;
+        for (int e0 = 0; e0 < nent; e0 += 256) {
+          uint32_t so[8], dlo[8], dch[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint2 en = rpk[e0 + k * 32 + lane];
+            const bool on = (int)(en.y >> 16) < nvalid;
+            so[k] = on ? (en.y & 0xffffu) * 2u : 0xffffffffu;
+            dlo[k] = en.x & 0xffffffu;
+            dch[k] = en.x >> 24;
+          }
+          for (int cl = warp; cl < tg.CH; cl += NWARPS) {
+            const int c = cs * tg.CH + cl;
+            const uint32_t srow = stg + (uint32_t)cl * cstride;
+            const uint32_t drow = sbase + (uint32_t)(x * C::TILE_BYTES + c * 128);
+            uint32_t val[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (so[k] != 0xffffffffu) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(val[k]) : "r"(srow + so[k]));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (so[k] != 0xffffffffu) sts_u16(drow + dlo[k] + (((dch[k] ^ (uint32_t)c) & 7u) << 4), val[k]);
+          }
+        }
+        __syncthreads();                                 // staging buffer fully consumed
+        if (tid == 0) {                                  // refill it with the load two positions ahead
+          const int nj = j + 2 < lpg ? j + 2 : j + 2 - lpg;
+          const long long ngrp = j + 2 < lpg ? grp : grp + gridDim.x;
+          if (ngrp < prm.ngroups) issue_load(ngrp, nj, pos + 2);
+        }
+      }
+    } else {
     // ---- gather (fused `window`): unit = (warp-item, tensor, 32-channel block)
     {
       const int units = mp.nwi * 3 * (D / CB);
@@ -241,6 +360,7 @@ tc_win_fwd_kernel(const WinParams prm) {
         const uint32_t dst = sbase + (uint32_t)((t_i * 3 + x) * C::TILE_BYTES + (rr >> 6) * C::BOX_BYTES + (rr & 7) * 2 + c0 * 128);
         gather_unit<CB>(tens[x] + (long long)c0 * N, so, N, dst, (uint32_t)((rr & 63) >> 3));
       }
+    }
     }
     fence_proxy_async();
     __syncthreads();
@@ -262,7 +382,7 @@ tc_win_fwd_kernel(const WinParams prm) {
       __syncwarp();
     }
     const long long gw = gw0 + (long long)ti * mp.G + wi;
-    const bool valid = wi < mp.G && gw < prm.nwin;
+    const bool valid = wi < mp.G && gw < prm.nwin && ti * mp.G + wi < nvalid;
     mbar_wait(bar_s, it & 1u);
     tc_fence_after();
 
@@ -768,9 +888,57 @@ bool make_map(const Geo& g, int NT, WinMap& mp) {
   return mp.nwi * 32 <= MAXE;
 }
 
+typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 5-D map over one (X, Y, Z, d, B) tensor (missing spatial dims = 1): box (BX, by, bz, d, 1), no swizzle,
+// zero fill out of bounds (= the zero padding of `window`, src/utils.jl:40)
+int make_win_tmap(CUtensorMap* tm, const void* base, int dtype, const Geo& g, int D, const TmaGeo& tg) {
+  static EncodeTiledFn5 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn5>(p);
+  });
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return FA_ERR_CUDA; }
+  const cuuint64_t dims[5] = {(cuuint64_t)g.s[0], (cuuint64_t)g.s[1], (cuuint64_t)g.s[2], (cuuint64_t)D, (cuuint64_t)g.B};
+  const cuuint64_t strides[4] = {(cuuint64_t)g.s[0] * 2, (cuuint64_t)g.s[0] * g.s[1] * 2, (cuuint64_t)g.N * 2, (cuuint64_t)g.N * D * 2};
+  const cuuint32_t box[5] = {(cuuint32_t)tg.BX, (cuuint32_t)tg.by, (cuuint32_t)tg.bz, (cuuint32_t)tg.CH, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == FA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(tm, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (windowed 5-D) failed (CUresult %d)", (int)r); return FA_ERR_CUDA; }
+  return FA_OK;
+}
+
+// can the TMA-gather variant take this geometry?  (exact-cover windows, 16-byte aligned rows, box fits the staging)
+template <int D, int NT>
+bool tma_gather_geo(const Geo& g, const WinMap& mp, TmaGeo& tg) {
+  using C = WCfg<D, NT, 1>;
+  if (g.stride != g.W || g.s[0] % 8 != 0) return false;
+  tg.TW = mp.nwc * g.W;
+  // the box starts at the 16-byte boundary at or below the first token: up to 7 extra tokens in front
+  const bool always_aligned = (mp.nwc * g.W) % 8 == 0 && g.pad % 8 == 0;
+  tg.BX = (tg.TW + (always_aligned ? 0 : 7) + 7) / 8 * 8;
+  tg.by = g.nd >= 2 ? g.W : 1;
+  tg.bz = g.nd >= 3 ? g.W : 1;
+  tg.RGN = tg.by * tg.bz;
+  tg.gpr = (g.o[0] + mp.nwc - 1) / mp.nwc;
+  tg.CH = D;
+  while (tg.CH > 8 && (long long)tg.BX * tg.by * tg.bz * tg.CH * 2 > C::STG_BYTES) tg.CH /= 2;
+  tg.ncs = D / tg.CH;
+  const long long bytes = (long long)tg.BX * tg.by * tg.bz * tg.CH * 2;
+  if (tg.BX > 256 || g.pad > 1024 || bytes > C::STG_BYTES || tg.RGN * tg.TW > C::RPK_MAX || tg.RGN * tg.BX + 8 > 65535) return false;
+  tg.box_bytes = (unsigned)bytes;
+  return true;
+}
+
 template <int D, int NT, int FMT>
 int launch_win_fwd(const Geo& g, const FwdArgs& a, cudaStream_t st) {
-  using C = WCfg<D, NT>;
   WinParams prm;
   prm.q = a.q; prm.k = a.k; prm.v = a.v; prm.y = a.o; prm.acc = a.acc; prm.l = a.l; prm.m = a.m;
   prm.g = g;
@@ -778,14 +946,37 @@ int launch_win_fwd(const Geo& g, const FwdArgs& a, cudaStream_t st) {
   prm.nwin = g.L * g.B;
   prm.ngroups = (prm.nwin + prm.mp.nwc - 1) / prm.mp.nwc;
   prm.scale_log2 = g.tau * LOG2E;
-  auto kern = tc_win_fwd_kernel<D, NT, FMT>;
-  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap tq, tk, tv;
+  memset(&tq, 0, sizeof(tq)); memset(&tk, 0, sizeof(tk)); memset(&tv, 0, sizeof(tv));
+  TmaGeo tg;
+  memset(&tg, 0, sizeof(tg));
+  static const int use_tma = [] { const char* e = getenv("FA_WIN_TMA"); return e ? atoi(e) : 0; }();
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) == 0;
+  if (D == 64 && use_tma && aligned && tma_gather_geo<D, NT>(g, prm.mp, tg)) {
+    using C = WCfg<D, NT, 1>;
+    const int dtype = FMT ? FA_BF16 : FA_F16;
+    int rc;
+    if ((rc = make_win_tmap(&tq, a.q, dtype, g, D, tg))) return rc;
+    if ((rc = make_win_tmap(&tk, a.k, dtype, g, D, tg))) return rc;
+    if ((rc = make_win_tmap(&tv, a.v, dtype, g, D, tg))) return rc;
+    prm.ngroups = (long long)tg.gpr * g.o[1] * g.o[2] * g.B;      // groups never straddle a window row
+    auto kern = tc_win_fwd_kernel<D, NT, FMT, 1>;
+    FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    const long long cap = (long long)sms * C::CTAS_PER_SM;
+    const unsigned grid = (unsigned)(prm.ngroups < cap ? prm.ngroups : cap);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tq, tk, tv, prm, tg);
+    FA_CUDA_TRY(cudaGetLastError());
+    return FA_OK;
+  }
+  using C = WCfg<D, NT, 0>;
+  auto kern = tc_win_fwd_kernel<D, NT, FMT, 0>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const long long cap = (long long)sms * C::CTAS_PER_SM;
   const unsigned grid = (unsigned)(prm.ngroups < cap ? prm.ngroups : cap);
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(prm);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tq, tk, tv, prm, tg);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
 }

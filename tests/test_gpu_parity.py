@@ -341,6 +341,15 @@ def test_windowed_bwd_tc(spatial, W, kws, d, dtype):
         assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dvv, dv2)
 
 
+def test_windowed_tma_gather_variant():
+    """Opt-in TMA-gather variant of the windowed forward (FA_WIN_TMA=1; the flag is read once per process, so
+    the checker runs in a subprocess): 1-D / 2-D / 3-D exact-cover windows, incl. the config-5 geometry, 2e-3."""
+    import os, subprocess, sys
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools", "check_win_tma.py")
+    r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=600, env=dict(os.environ, FA_WIN_TMA="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_windowed_config5_geometry_tc():
     """BASELINE config 5 geometry (64^3 volume, W = 5, stride 5, pad 3: 2744 exact-cover windows of 125
     tokens, d = 64) at batch 1, bf16, forward and backward against the float64 oracle; plus the
