@@ -64,20 +64,29 @@ Geo dense_geo(int64_t N, int64_t d, int64_t dv, int64_t B) {
   return g;
 }
 
+// slab_pad_lo >= 0 makes the geometry a SLAB of a larger volume along the slowest spatial dim: `dims` are the
+// slab's own extents, the first window of that dim starts slab_pad_lo planes in front of the slab and
+// slab_nwin windows are taken (instead of the NNlib output size); the other dims keep `pad`.
 int windowed_geo(Geo& g, int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B, int64_t W,
-                 int64_t stride, int64_t pad) {
+                 int64_t stride, int64_t pad, int64_t slab_pad_lo = -1, int64_t slab_nwin = 0) {
   if (ndim < 1 || ndim > 3 || !dims) { set_error("ndim must be 1, 2 or 3"); return FA_ERR_INVALID; }
   if (W <= 0 || stride <= 0 || pad < 0) { set_error("need W > 0, stride > 0, pad >= 0"); return FA_ERR_INVALID; }
   memset(&g, 0, sizeof(g));
   g.mode = MODE_WINDOWED; g.d = (int)d; g.dv = (int)dv; g.B = B; g.nd = ndim;
-  g.W = (int)W; g.stride = (int)stride; g.pad = (int)pad;
+  g.W = (int)W; g.stride = (int)stride;
+  for (int k = 0; k < 3; ++k) g.padv[k] = (int)pad;
   g.tau = 1.0f / sqrtf((float)d);
   long long N = 1, L = 1, WD = 1;
   for (int k = 0; k < 3; ++k) { g.s[k] = 1; g.o[k] = 1; }
   for (int k = 0; k < ndim; ++k) {
     if (dims[k] <= 0 || dims[k] > 0x7fffffffLL) { set_error("bad spatial extent"); return FA_ERR_INVALID; }
-    const long long o = (dims[k] + 2 * pad - W) / stride + 1;      // NNlib output size
-    if (dims[k] + 2 * pad < W || o <= 0) { set_error("window (%lld) larger than padded extent (%lld + 2*%lld)", (long long)W, (long long)dims[k], (long long)pad); return FA_ERR_INVALID; }
+    long long o = (dims[k] + 2 * pad - W) / stride + 1;            // NNlib output size
+    if (slab_pad_lo >= 0 && k == ndim - 1) {
+      if (slab_nwin <= 0 || slab_pad_lo >= W || (slab_nwin - 1) * stride - slab_pad_lo >= dims[k]) {
+        set_error("slab: need nwin > 0, pad_lo < W and the last window starting inside the slab"); return FA_ERR_INVALID;
+      }
+      g.padv[k] = (int)slab_pad_lo; o = slab_nwin;
+    } else if (dims[k] + 2 * pad < W || o <= 0) { set_error("window (%lld) larger than padded extent (%lld + 2*%lld)", (long long)W, (long long)dims[k], (long long)pad); return FA_ERR_INVALID; }
     g.s[k] = (int)dims[k]; g.o[k] = (int)o;
     N *= dims[k]; L *= o; WD *= W;
     if (WD > 0x7fffffffLL || N > 0x7fffffffLL) { set_error("window or volume too large"); return FA_ERR_INVALID; }
@@ -91,7 +100,7 @@ int windowed_geo(Geo& g, int ndim, const int64_t* dims, int64_t d, int64_t dv, i
 bool full_cover(const Geo& g) {
   for (int k = 0; k < g.nd; ++k)
     for (int pos = 0; pos < g.s[k]; ++pos) {
-      Geo g1 = g; g1.nd = 1; g1.s[0] = g.s[k]; g1.o[0] = g.o[k];
+      Geo g1 = g; g1.nd = 1; g1.s[0] = g.s[k]; g1.o[0] = g.o[k]; g1.padv[0] = g.padv[k];
       if (window_count_at(g1, pos) == 0) return false;
     }
   return true;
@@ -237,24 +246,30 @@ int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o,
 }
 
 // ------------------------------------------------------------------------------ windowed
+static size_t windowed_fwd_ws(const Geo& g) {
+  return g.overlap ? align256((size_t)g.N * g.dv * g.B * sizeof(float)) : 256;
+}
+static size_t windowed_bwd_ws(const Geo& g) {
+  size_t bytes = align256((size_t)g.WD * g.L * g.B * sizeof(float));                 // delta per window slot
+  if (g.overlap) bytes += 2 * align256((size_t)g.N * g.d * g.B * sizeof(float)) + align256((size_t)g.N * g.dv * g.B * sizeof(float));
+  return bytes;
+}
+
 size_t fa_workspace_bytes_windowed_fwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
                                        int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
   (void)dtype; (void)flags;
   Geo g;
   if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
-  return g.overlap ? align256((size_t)g.N * dv * B * sizeof(float)) : 256;
+  return windowed_fwd_ws(g);
 }
 
-int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float* l, float* m,
-                    int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
-                    int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  Geo g;
-  int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
-  if (rc) return rc;
+static int windowed_fwd_impl(const Geo& g, const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                             int dtype, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  const int64_t d = g.d, dv = g.dv, B = g.B;
+  int rc;
   if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
   if (!q || !k || !v || !y || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  if (g.overlap && (!workspace || workspace_bytes < fa_workspace_bytes_windowed_fwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags))) {
+  if (g.overlap && (!workspace || workspace_bytes < windowed_fwd_ws(g))) {
     set_error("workspace too small"); return FA_ERR_WORKSPACE;
   }
   if ((rc = need_device())) return rc;
@@ -273,27 +288,32 @@ int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float*
   return FA_OK;
 }
 
-size_t fa_workspace_bytes_windowed_bwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
-                                       int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
-  (void)dtype; (void)flags;
-  Geo g;
-  if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
-  size_t bytes = align256((size_t)g.WD * g.L * B * sizeof(float));                 // delta per window slot
-  if (g.overlap) bytes += 2 * align256((size_t)g.N * d * B * sizeof(float)) + align256((size_t)g.N * dv * B * sizeof(float));
-  return bytes;
-}
-
-int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y,
-                    const float* l, const float* m, void* dq, void* dk, void* dv_out,
+int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float* l, float* m,
                     int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
                     int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
                     void* workspace, size_t workspace_bytes, void* stream) {
   Geo g;
   int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
   if (rc) return rc;
+  return windowed_fwd_impl(g, q, k, v, y, l, m, dtype, flags, workspace, workspace_bytes, stream);
+}
+
+size_t fa_workspace_bytes_windowed_bwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                                       int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
+  (void)dtype; (void)flags;
+  Geo g;
+  if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
+  return windowed_bwd_ws(g);
+}
+
+static int windowed_bwd_impl(const Geo& g, const void* q, const void* k, const void* v, const void* d_y,
+                             const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                             int dtype, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  const int64_t d = g.d, dv = g.dv, B = g.B;
+  int rc;
   if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
   if (!q || !k || !v || !d_y || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  if (!workspace || workspace_bytes < fa_workspace_bytes_windowed_bwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags)) {
+  if (!workspace || workspace_bytes < windowed_bwd_ws(g)) {
     set_error("workspace too small"); return FA_ERR_WORKSPACE;
   }
   if ((rc = need_device())) return rc;
@@ -323,6 +343,83 @@ int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y
     FA_CUDA_TRY(cudaMemsetAsync(dv_out, 0, (size_t)g.N * dv * B * esz, st));
   }
   return tc ? tc_win_bwd(g, a, dtype, st) : simt_bwd(g, a, dtype, st);
+}
+
+int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y,
+                    const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                    int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                    int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
+  if (rc) return rc;
+  return windowed_bwd_impl(g, q, k, v, d_y, l, m, dq, dk, dv_out, dtype, flags, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------ windowed, one volume over several GPUs
+// Non-overlapping windows (stride >= W) are independent, so a single volume splits into SLABS along its
+// slowest spatial dim on window boundaries with no exchange at all: rank r takes the window
+// planes [win_lo, win_hi) of that dim and holds exactly the token planes [plane_lo, plane_hi) they read.
+// plan[5] = {plane_lo, plane_hi, win_lo, win_hi, pad_lo}; pad_lo = zero planes in front of the slab (the
+// volume's own padding, non-zero only for the rank that owns the first window).
+int fa_windowed_slab_plan(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                          int rank, int nranks, int64_t* plan) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, 1, 1, 1, W, stride, pad);
+  if (rc) return rc;
+  if (!plan || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bad rank / nranks / plan"); return FA_ERR_INVALID; }
+  if (stride < W) { set_error("slab split needs non-overlapping windows (stride >= W); overlapping windows need a halo reduce"); return FA_ERR_UNSUPPORTED; }
+  if (pad >= W) { set_error("slab split needs pad < W"); return FA_ERR_UNSUPPORTED; }
+  const int ks = ndim - 1;
+  const int64_t S = dims[ks], nw = g.o[ks];
+  int64_t lo = 0, cnt = 0;
+  if ((rc = fa_shard_batch(nw, nranks, rank, &lo, &cnt))) return rc;
+  const int64_t hi = lo + cnt;
+  plan[2] = lo; plan[3] = hi;
+  if (cnt <= 0) { plan[0] = plan[1] = 0; plan[4] = 0; return FA_OK; }          // more ranks than window planes
+  // slab boundary in front of window w = its first plane (clipped): the slabs tile the volume, and planes in
+  // the gaps between windows (stride > W) or behind the last window stay with the slab in front of them --
+  // uncovered there (y = NaN, zero gradient) exactly as in the one-GPU call
+  auto bnd = [&](int64_t w) { const int64_t x = w * stride - pad; return x < 0 ? (int64_t)0 : (x > S ? S : x); };
+  plan[0] = lo == 0 ? 0 : bnd(lo);
+  plan[1] = hi == nw ? S : bnd(hi);
+  plan[4] = plan[0] - (lo * stride - pad);
+  return FA_OK;
+}
+
+static int slab_geo(Geo& g, int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B, int64_t W,
+                    int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin) {
+  if (stride < W) { set_error("slab split needs non-overlapping windows (stride >= W)"); return FA_ERR_UNSUPPORTED; }
+  if (pad_lo < 0) { set_error("slab: pad_lo must be >= 0"); return FA_ERR_INVALID; }
+  return windowed_geo(g, ndim, slab_dims, d, dv, B, W, stride, pad, pad_lo, nwin);
+}
+
+size_t fa_workspace_bytes_windowed_slab_bwd(int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                                            int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin) {
+  Geo g;
+  if (slab_geo(g, ndim, slab_dims, d, dv, B, W, stride, pad, pad_lo, nwin)) return 0;
+  return windowed_bwd_ws(g);
+}
+
+int fa_windowed_slab_fwd(const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                         int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
+                         int dtype, int flags, void* stream) {
+  Geo g;
+  int rc = slab_geo(g, ndim, slab_dims, d, dv, B, W, stride, pad, pad_lo, nwin);
+  if (rc) return rc;
+  return windowed_fwd_impl(g, q, k, v, y, l, m, dtype, flags, nullptr, 0, stream);
+}
+
+int fa_windowed_slab_bwd(const void* q, const void* k, const void* v, const void* d_y,
+                         const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                         int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
+                         int dtype, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  Geo g;
+  int rc = slab_geo(g, ndim, slab_dims, d, dv, B, W, stride, pad, pad_lo, nwin);
+  if (rc) return rc;
+  return windowed_bwd_impl(g, q, k, v, d_y, l, m, dq, dk, dv_out, dtype, flags, workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------ unfold / fold

@@ -28,7 +28,8 @@ struct Geo {
   int s[3];          // spatial extents (windowed), s[0] fastest
   int o[3];          // windows per dim (windowed)
   int W;             // window size (circulant: band width; windowed: per-dim window)
-  int stride, pad;   // windowed
+  int stride;        // windowed
+  int padv[3];       // windowed: zero padding in front of each spatial dim (equal unless the volume is a slab)
   int WD;            // W^nd slots per window (windowed)
   int p;             // (W-1)/2 (circulant)
   int overlap;       // windowed: 1 if a position can be covered by >1 window (fold needs +=)
@@ -51,7 +52,7 @@ __host__ __device__ inline long long window_slot_token(const Geo& g, long long w
   for (int k = 0; k < g.nd; ++k) {
     const int wk = (int)(win % g.o[k]);  win /= g.o[k];
     const int kk = slot % g.W;           slot /= g.W;
-    const int pos = wk * g.stride - g.pad + kk;
+    const int pos = wk * g.stride - g.padv[k] + kk;
     if (pos < 0 || pos >= g.s[k]) return -1;
     tok += pos * mult;
     mult *= g.s[k];
@@ -64,7 +65,7 @@ __host__ __device__ inline int window_count_at(const Geo& g, long long tok) {
   int cnt = 1;
   for (int k = 0; k < g.nd; ++k) {
     const int pos = (int)(tok % g.s[k]);  tok /= g.s[k];
-    const int a = pos + g.pad;                         // 0 <= a - w*stride < W
+    const int a = pos + g.padv[k];                      // 0 <= a - w*stride < W
     int wmax = a / g.stride;
     if (wmax > g.o[k] - 1) wmax = g.o[k] - 1;
     int lo = a - g.W + 1;

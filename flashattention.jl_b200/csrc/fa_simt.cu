@@ -474,7 +474,7 @@ __global__ void window_scatter_kernel(const Geo g, const T* __restrict__ xw, T* 
     bool any = true;
     for (int k = 0; k < g.nd; ++k) {
       pos[k] = (int)(tok % g.s[k]); tok /= g.s[k];
-      const int av = pos[k] + g.pad;
+      const int av = pos[k] + g.padv[k];
       int wmax = av / g.stride; if (wmax > g.o[k] - 1) wmax = g.o[k] - 1;
       const int lo = av - g.W + 1;
       wlo[k] = lo <= 0 ? 0 : (lo + g.stride - 1) / g.stride;
@@ -490,7 +490,7 @@ __global__ void window_scatter_kernel(const Geo g, const T* __restrict__ xw, T* 
             long long w = 0, wm = 1; int kap = 0, km = 1;
             for (int k = 0; k < g.nd; ++k) {
               w += wi[k] * wm; wm *= g.o[k];
-              kap += (pos[k] + g.pad - wi[k] * g.stride) * km; km *= g.W;
+              kap += (pos[k] + g.padv[k] - wi[k] * g.stride) * km; km *= g.W;
             }
             sum += to_f32<T>(xw[((b * g.L + w) * g.d + c) * g.WD + kap]);
           }

@@ -166,7 +166,7 @@ __device__ __forceinline__ void build_wininfo(const Geo& g, const WinMap& mp, lo
       for (int k = 0; k < 3; ++k) {
         const int wk = w % g.o[k];
         w /= g.o[k];
-        o3[k] = (k < g.nd) ? wk * g.stride - g.pad : 0;
+        o3[k] = (k < g.nd) ? wk * g.stride - g.padv[k] : 0;
       }
       wi4 = make_int4(o3[0], o3[1], o3[2], (int)b);
     }
@@ -276,9 +276,9 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     const int wz = (int)(r2 % g.o[2]);
     b = (int)(r2 / g.o[2]);
     gw0 = (((long long)b * g.o[2] + wz) * g.o[1] + wy) * g.o[0] + wx0;
-    x0 = wx0 * g.stride - g.pad;                      // the box itself starts at the 16-byte boundary below x0
-    y0 = g.nd >= 2 ? wy * g.stride - g.pad : 0;
-    z0 = g.nd >= 3 ? wz * g.stride - g.pad : 0;
+    x0 = wx0 * g.stride - g.padv[0];                     // the box itself starts at the 16-byte boundary below x0
+    y0 = g.nd >= 2 ? wy * g.stride - g.padv[1] : 0;
+    z0 = g.nd >= 3 ? wz * g.stride - g.padv[2] : 0;
   };
   // load number `pos` of this CTA (lpg = 3 * ncs per group: q, k, v in channel slices) goes to staging buffer pos & 1.
   // TMA wants the innermost coordinate 16-byte aligned: the box starts at the multiple of 8 below x0.
@@ -922,7 +922,7 @@ bool tma_gather_geo(const Geo& g, const WinMap& mp, TmaGeo& tg) {
   if (g.stride != g.W || g.s[0] % 8 != 0) return false;
   tg.TW = mp.nwc * g.W;
   // the box starts at the 16-byte boundary at or below the first token: up to 7 extra tokens in front
-  const bool always_aligned = (mp.nwc * g.W) % 8 == 0 && g.pad % 8 == 0;
+  const bool always_aligned = (mp.nwc * g.W) % 8 == 0 && g.padv[0] % 8 == 0;
   tg.BX = (tg.TW + (always_aligned ? 0 : 7) + 7) / 8 * 8;
   tg.by = g.nd >= 2 ? g.W : 1;
   tg.bz = g.nd >= 3 ? g.W : 1;
@@ -932,7 +932,7 @@ bool tma_gather_geo(const Geo& g, const WinMap& mp, TmaGeo& tg) {
   while (tg.CH > 8 && (long long)tg.BX * tg.by * tg.bz * tg.CH * 2 > C::STG_BYTES) tg.CH /= 2;
   tg.ncs = D / tg.CH;
   const long long bytes = (long long)tg.BX * tg.by * tg.bz * tg.CH * 2;
-  if (tg.BX > 256 || g.pad > 1024 || bytes > C::STG_BYTES || tg.RGN * tg.TW > C::RPK_MAX || tg.RGN * tg.BX + 8 > 65535) return false;
+  if (tg.BX > 256 || g.padv[0] > 1024 || bytes > C::STG_BYTES || tg.RGN * tg.TW > C::RPK_MAX || tg.RGN * tg.BX + 8 > 65535) return false;
   tg.box_bytes = (unsigned)bytes;
   return true;
 }

@@ -79,6 +79,10 @@ def _load():
         "fa_windowed_fwd": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
         "fa_workspace_bytes_windowed_bwd": (sz, [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci]),
         "fa_windowed_bwd": (ci, [vp] * 9 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
+        "fa_windowed_slab_plan": (ci, [ci, pi64, i64, i64, i64, ci, ci, pi64]),
+        "fa_windowed_slab_fwd": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp]),
+        "fa_workspace_bytes_windowed_slab_bwd": (sz, [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64]),
+        "fa_windowed_slab_bwd": (ci, [vp] * 9 + [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
         "fa_window": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_unwindow": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_softmax": (ci, [vp, vp, i64, i64, i64, ci, ci, vp]),
@@ -108,7 +112,8 @@ EXPORTED_SYMBOLS = (
     "fa_workspace_bytes_windowed_bwd fa_windowed_bwd fa_window fa_unwindow fa_softmax fa_dense_fwd_host "
     "fa_circulant_fwd_host fa_windowed_fwd_host fa_release_host_staging fa_shard_batch fa_merge_partials "
     "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd "
-    "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd").split()
+    "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd "
+    "fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd").split()
 
 
 def _check(rc: int, what: str):
@@ -416,6 +421,77 @@ def windowed_fa_backward(q, k, v, dy, l, m, windowsize: int, stride=None, pad=No
         _check(lib.fa_windowed_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(dy), _ptr(l), _ptr(m), _ptr(dq), _ptr(dk), _ptr(dvv),
                                    len(spatial), dims, d, dv, B, W, stride, pad, _dt(q), flags,
                                    _ptr(ws), ws.numel(), _stream(q)), "fa_windowed_bwd")
+    return dq, dk, dvv
+
+
+class SlabPlan(tuple):
+    """(plane_lo, plane_hi, win_lo, win_hi, pad_lo) of one rank's slab (see :func:`windowed_slab_plan`)."""
+    plane_lo = property(lambda s: s[0]); plane_hi = property(lambda s: s[1])
+    win_lo = property(lambda s: s[2]); win_hi = property(lambda s: s[3]); pad_lo = property(lambda s: s[4])
+    nwin = property(lambda s: s[3] - s[2])
+
+
+def windowed_slab_plan(spatial, windowsize: int, stride=None, pad=None, rank: int = 0, nranks: int = 1) -> SlabPlan:
+    """One volume over several GPUs: non-overlapping windows are independent, so the volume is cut
+    into slabs along its slowest spatial dim on window boundaries and needs no exchange.  Rank ``rank`` takes the
+    windows ``[win_lo, win_hi)`` of that dim and holds the token planes ``[plane_lo, plane_hi)``."""
+    W = int(windowsize)
+    stride, pad = _win_kws(W, stride, pad)
+    plan = _i64arr([0] * 5)
+    _check(lib.fa_windowed_slab_plan(len(spatial), _i64arr(spatial), W, stride, pad, int(rank), int(nranks), plan),
+           "fa_windowed_slab_plan")
+    return SlabPlan(int(x) for x in plan)
+
+
+def slab_planes(x, plan: SlabPlan):
+    """The planes ``[plane_lo, plane_hi)`` of the slowest spatial dim of ``x :: (s.., d, B)``, column-major."""
+    ax = x.ndim - 3
+    return jl_array(x.narrow(ax, plan.plane_lo, plan.plane_hi - plan.plane_lo))
+
+
+def windowed_fa_slab(q, k, v, windowsize: int, plan: SlabPlan, stride=None, pad=None, flags: int = 0):
+    """:func:`windowed_fa` on one slab ``q, k, v :: (s.., planes, d, B)`` of a volume split by
+    :func:`windowed_slab_plan`: ``y`` for the slab's planes and ``l, m :: (W^D, 1, L_slab, B)`` for its windows
+    (a contiguous range of the volume's window index), equal bit for bit to the same entries of the one-GPU call."""
+    _same(q, k, v)
+    q, k, v = (jl_array(t) for t in (q, k, v))
+    W = int(windowsize)
+    stride, pad = _win_kws(W, stride, pad)
+    spatial = tuple(int(s) for s in q.shape[:-2])
+    d, dv, B = int(q.shape[-2]), int(v.shape[-2]), int(q.shape[-1])
+    if spatial[-1] != plan.plane_hi - plan.plane_lo:
+        raise FaError("windowed_fa_slab: the slab must hold exactly the planes [plane_lo, plane_hi) of its plan")
+    nw = window_counts(spatial[:-1], W, stride, pad) + (plan.nwin,) if len(spatial) > 1 else (plan.nwin,)
+    L = 1
+    for n in nw:
+        L *= n
+    WD = W ** len(spatial)
+    y = jl_empty(spatial + (dv, B), q.dtype, q.device)
+    l = jl_empty((WD, 1, L, B), torch.float32, q.device)
+    m = jl_empty((WD, 1, L, B), torch.float32, q.device)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_windowed_slab_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(y), _ptr(l), _ptr(m), len(spatial), _i64arr(spatial),
+                                        d, dv, B, W, stride, pad, plan.pad_lo, plan.nwin, _dt(q), flags, _stream(q)),
+               "fa_windowed_slab_fwd")
+    return y, l, m
+
+
+def windowed_fa_slab_backward(q, k, v, dy, l, m, windowsize: int, plan: SlabPlan, stride=None, pad=None, flags: int = 0):
+    """Backward of :func:`windowed_fa_slab`: gradients of the slab's own planes (no exchange needed)."""
+    _same(q, k, v, dy)
+    q, k, v, dy = (jl_array(t) for t in (q, k, v, dy))
+    l, m = (jl_array(t, torch.float32) for t in (l, m))
+    W = int(windowsize)
+    stride, pad = _win_kws(W, stride, pad)
+    spatial = tuple(int(s) for s in q.shape[:-2])
+    d, dv, B = int(q.shape[-2]), int(v.shape[-2]), int(q.shape[-1])
+    dims = _i64arr(spatial)
+    dq, dk, dvv = (jl_empty(t.shape, t.dtype, t.device) for t in (q, k, v))
+    ws = _workspace(lib.fa_workspace_bytes_windowed_slab_bwd(len(spatial), dims, d, dv, B, W, stride, pad, plan.pad_lo, plan.nwin), q.device)
+    with torch.cuda.device(q.device):
+        _check(lib.fa_windowed_slab_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(dy), _ptr(l), _ptr(m), _ptr(dq), _ptr(dk), _ptr(dvv),
+                                        len(spatial), dims, d, dv, B, W, stride, pad, plan.pad_lo, plan.nwin, _dt(q), flags,
+                                        _ptr(ws), ws.numel(), _stream(q)), "fa_windowed_slab_bwd")
     return dq, dk, dvv
 
 

@@ -59,3 +59,76 @@ function ring_dense_fa_backward(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T
     CUDA.synchronize()
     return dQ, dK, dV
 end
+
+# ---- one volume over several GPUs: windowed attention with non-overlapping windows (stride >= W) splits into
+# slabs along the slowest spatial dim on window boundaries; no exchange (SURVEY 8e).
+
+"Slab of rank `rank` (0-based): token planes `plane_lo:plane_hi-1` (0-based, slowest spatial dim), windows `win_lo:win_hi-1`, `pad_lo` zero planes in front."
+struct SlabPlan
+    plane_lo::Int64
+    plane_hi::Int64
+    win_lo::Int64
+    win_hi::Int64
+    pad_lo::Int64
+end
+
+function windowed_slab_plan(spatial, windowsize; stride=windowsize, pad=(windowsize-1)÷2, rank::Integer=0, nranks::Integer=1)
+    dims = Int64[spatial...]
+    plan = zeros(Int64, 5)
+    rc = ccall(sym(:fa_windowed_slab_plan), Cint, (Cint, Ptr{Int64}, Int64, Int64, Int64, Cint, Cint, Ptr{Int64}),
+               length(dims), dims, windowsize, stride, pad, rank, nranks, plan)
+    check(rc, "fa_windowed_slab_plan")
+    return SlabPlan(plan...)
+end
+
+"The planes of `x :: (s.., d, B)` that `plan` assigns to its rank (a contiguous copy)."
+slab_planes(x::AbstractArray{T, N}, plan::SlabPlan) where {T, N} =
+    copy(selectdim(x, N - 2, plan.plane_lo+1:plan.plane_hi))
+
+"""
+    windowed_fa_slab(q, k, v, windowsize, plan; stride, pad) -> (y, l, m)
+
+`windowed_fa` on one slab of a volume cut by `windowed_slab_plan`: `y` for the slab's planes, `l, m` for its
+windows (a contiguous range of the volume's window index) -- the same bits the one-GPU call produces there.
+"""
+function windowed_fa_slab(q::CuArray{T, N}, k::CuArray{T, N}, v::CuArray{T, N}, windowsize, plan::SlabPlan;
+                          stride=windowsize, pad=(windowsize-1)÷2, flags::Integer=0) where {T, N}
+    D = N - 2
+    dims = Int64[size(q, i) for i in 1:D]
+    d, dv, B = size(q, N-1), size(v, N-1), size(q, N)
+    nw = plan.win_hi - plan.win_lo
+    nwin = [(dims[i] + 2pad - windowsize) ÷ stride + 1 for i in 1:D-1]
+    L, WD = prod(nwin; init=1) * nw, windowsize^D
+    y = similar(q, size(q)[1:D]..., dv, B)
+    l = CUDA.zeros(Float32, WD, 1, L, B)
+    m = CUDA.zeros(Float32, WD, 1, L, B)
+    rc = ccall(sym(:fa_windowed_slab_fwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}),
+               devptr(q), devptr(k), devptr(v), devptr(y), devptr(l), devptr(m),
+               D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw, fa_dtype(T), Cint(flags), current_stream())
+    check(rc, "fa_windowed_slab_fwd")
+    return y, l, m
+end
+
+function windowed_fa_slab_backward(q::CuArray{T, N}, k::CuArray{T, N}, v::CuArray{T, N}, dy::CuArray{T, N},
+                                   l::CuArray{Float32, 4}, m::CuArray{Float32, 4}, windowsize, plan::SlabPlan;
+                                   stride=windowsize, pad=(windowsize-1)÷2, flags::Integer=0) where {T, N}
+    D = N - 2
+    dims = Int64[size(q, i) for i in 1:D]
+    d, dv, B = size(q, N-1), size(v, N-1), size(q, N)
+    nw = plan.win_hi - plan.win_lo
+    dq, dk, dvv = similar(q), similar(k), similar(v)
+    nws = ccall(sym(:fa_workspace_bytes_windowed_slab_bwd), Csize_t,
+                (Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64),
+                D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw)
+    ws = CuArray{UInt8}(undef, max(nws, 256))
+    rc = ccall(sym(:fa_windowed_slab_bwd), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+               devptr(q), devptr(k), devptr(v), devptr(dy), devptr(l), devptr(m), devptr(dq), devptr(dk), devptr(dvv),
+               D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw, fa_dtype(T), Cint(flags),
+               devptr(ws), length(ws), current_stream())
+    check(rc, "fa_windowed_slab_bwd")
+    return dq, dk, dvv
+end

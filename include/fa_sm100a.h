@@ -131,6 +131,29 @@ int fa_windowed_bwd(const void* q, const void* k, const void* v, const void* d_y
                     int64_t W, int64_t stride, int64_t pad, int dtype, int flags,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- windowed, ONE volume over several GPUs (slab split on window boundaries, no exchange).
+ *      Non-overlapping windows only (stride >= W, pad < W).  fa_windowed_slab_plan (host): rank r of nranks takes
+ *      the windows [win_lo, win_hi) of the slowest spatial dim and holds the token planes [plane_lo, plane_hi)
+ *      of that dim; plan[5] = {plane_lo, plane_hi, win_lo, win_hi, pad_lo}.  The slab calls then see a volume
+ *      of extents slab_dims (= dims with the slowest one replaced by plane_hi - plane_lo), `pad_lo` zero planes
+ *      in front of it and `nwin` = win_hi - win_lo windows along it; the other dims keep `pad`.  Outputs:
+ *      y :: (slab_dims.., dv, B), l,m :: (W^D, 1, L_slab, B) -- the windows of a slab are a contiguous range of
+ *      the volume's window index (src/utils.jl:36-44 enumerates windows x-fastest).  Mirrors what a caller of
+ *      windowed_fa (src/windowed.jl:3-23) would get on the whole volume, bit for bit. */
+int fa_windowed_slab_plan(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                          int rank, int nranks, int64_t* plan);
+int fa_windowed_slab_fwd(const void* q, const void* k, const void* v, void* y, float* l, float* m,
+                         int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
+                         int dtype, int flags, void* stream);
+size_t fa_workspace_bytes_windowed_slab_bwd(int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                                            int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin);
+int fa_windowed_slab_bwd(const void* q, const void* k, const void* v, const void* d_y,
+                         const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                         int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
+                         int dtype, int flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- standalone unfold/fold: window / unwindow (src/utils.jl:36-54) --------------------- */
 int fa_window(const void* x, void* xw, int ndim, const int64_t* dims, int64_t d, int64_t B,
               int64_t W, int64_t stride, int64_t pad, int dtype, void* stream);

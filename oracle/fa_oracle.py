@@ -349,6 +349,73 @@ def windowed_backward(q, k, v, dy, W, stride=None, pad=None):
 
 
 # --------------------------------------------------------------------------------------
+# one volume over several ranks: slab split on window boundaries (no reference code --
+# windows of src/utils.jl:36-44 with stride >= W never share a token, so whole window planes can be
+# handed to different ranks and nothing is exchanged)
+# --------------------------------------------------------------------------------------
+def windowed_slab_plan(spatial, W, stride=None, pad=None, rank=0, nranks=1):
+    """``(plane_lo, plane_hi, win_lo, win_hi, pad_lo)`` of rank ``rank``, by brute force from the window
+    index set: the window planes of the slowest dim are dealt out in contiguous balanced ranges; a token
+    plane belongs to the window plane that reads it, an unread one to the nearest window plane in front
+    of it (plane 0 side: the first)."""
+    stride, pad = _win_kws(W, stride, pad)
+    assert stride >= W > pad
+    S = spatial[-1]
+    nw = window_counts(spatial, W, stride, pad)[-1]
+    base, rem = divmod(nw, nranks)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    if hi <= lo:
+        return (0, 0, lo, hi, 0)
+    owner = np.full(S, -1)
+    for w in range(nw):
+        for t in range(W):
+            z = w * stride - pad + t
+            if 0 <= z < S:
+                owner[z] = w
+    for z in range(S):                       # unread planes: owner of the nearest read plane in front
+        if owner[z] < 0:
+            owner[z] = owner[z - 1] if z > 0 and owner[z - 1] >= 0 else 0
+    mine = np.nonzero((owner >= lo) & (owner < hi))[0]
+    plane_lo, plane_hi = int(mine[0]), int(mine[-1]) + 1
+    assert len(mine) == plane_hi - plane_lo
+    return (plane_lo, plane_hi, lo, hi, plane_lo - (lo * stride - pad))
+
+
+def _slab_embed(x, W, stride, pad, pad_lo, nwin):
+    """Slab ``(s.., planes, d, B)`` -> explicitly zero-padded volume on which ``window(.; pad=0)`` yields the slab's windows."""
+    x = _F(x)
+    spatial = x.shape[:-2]
+    D = len(spatial)
+    want = (nwin - 1) * stride + W                      # planes the slab's windows span
+    widths = [(pad, pad)] * (D - 1) + [(pad_lo, max(0, want - pad_lo - spatial[-1]))] + [(0, 0), (0, 0)]
+    xp = np.pad(x, widths)
+    sl = [slice(None)] * x.ndim
+    sl[D - 1] = slice(0, want)                          # planes behind the last window are not read
+    return _F(xp[tuple(sl)]), widths
+
+
+def windowed_fa_slab(q, k, v, W, stride, pad, pad_lo, nwin, threads: int = 1):
+    """``windowed_fa`` restricted to one slab: the slab's planes of ``y`` and its windows' ``l, m``."""
+    stride, pad = _win_kws(W, stride, pad)
+    spatial = q.shape[:-2]
+    D = len(spatial)
+    (qp, widths), (kp, _), (vp, _) = (_slab_embed(t, W, stride, pad, pad_lo, nwin) for t in (q, k, v))
+    yp, l, m = windowed_fa(qp, kp, vp, W, stride=stride, pad=0, threads=threads)
+    # crop the explicit padding; planes behind the last window (cut off above) are unread: 0/0 = NaN
+    sl = [slice(None)] * yp.ndim
+    for ax in range(D - 1):
+        sl[ax] = slice(pad, pad + spatial[ax])
+    have = min(spatial[-1], yp.shape[D - 1] - pad_lo)
+    sl[D - 1] = slice(pad_lo, pad_lo + have)
+    y = yp[tuple(sl)]
+    if have < spatial[-1]:
+        tail = list(y.shape); tail[D - 1] = spatial[-1] - have
+        y = np.concatenate([y, np.full(tail, np.nan, dtype=y.dtype)], axis=D - 1)
+    return _F(y), l, m
+
+
+# --------------------------------------------------------------------------------------
 # circulant (1-D)
 # --------------------------------------------------------------------------------------
 def circshift_index(m: int, s: int, M: int) -> int:

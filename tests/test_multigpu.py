@@ -5,7 +5,10 @@ K/V token blocks passed rank -> rank+1 while each rank merges partial (O, l, m) 
 of src/dense.jl:82-91 -- run with REAL send/recv between two processes, the oracle standing in for the
 block kernel (the CUDA kernels cannot run on the CPU and there is no fallback).
 GPU: fa_ring_dense_fwd on one rank (degenerate ring) and, when two GPUs are visible, on two ranks over
-NCCL, against the oracle on the whole sequence."""
+NCCL, against the oracle on the whole sequence.
+One volume over several ranks (windowed, non-overlapping windows): the slab plan against its brute-force oracle,
+slabs computed by two gloo processes assembling to the whole-volume oracle result, and on the GPU the slab
+kernels reproducing the one-GPU call bit for bit."""
 import os
 import socket
 import sys
@@ -92,6 +95,83 @@ def test_ring_schedule_gloo_world2():
     l = np.concatenate([out[r][1].numpy() for r in range(world)])
     m = np.concatenate([out[r][2].numpy() for r in range(world)])
     assert np.abs(y - y0).max() < 1e-12 and np.abs(l / l0 - 1).max() < 1e-12 and np.abs(m - m0).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------- windowed slabs
+SLAB_GEOS = [((64, 64, 64), 5, 5, 3), ((64, 64), 7, 7, 3), ((16,), 4, 4, 0), ((20, 9), 3, 4, 1), ((10,), 5, 5, 2),
+             ((12, 13), 5, 5, 2), ((9, 31), 4, 6, 3), ((7, 8, 30), 3, 3, 1), ((5, 40), 2, 7, 1)]
+
+
+def test_windowed_slab_plan_matches_oracle_and_tiles_the_volume():
+    import fa_sm100a as fa
+    for spatial, W, stride, pad in SLAB_GEOS:
+        nw = fo.window_counts(spatial, W, stride, pad)[-1]
+        for G in (1, 2, 3, 4, 8):
+            plans = [fa.windowed_slab_plan(spatial, W, stride, pad, r, G) for r in range(G)]
+            for r, pl in enumerate(plans):
+                assert tuple(pl) == tuple(fo.windowed_slab_plan(spatial, W, stride, pad, r, G))
+            live = [pl for pl in plans if pl.nwin > 0]
+            assert live[0].plane_lo == 0 and live[-1].plane_hi == spatial[-1] and live[0].win_lo == 0 and live[-1].win_hi == nw
+            for a, b in zip(live, live[1:]):
+                assert a.plane_hi == b.plane_lo and a.win_hi == b.win_lo
+            assert max(pl.nwin for pl in plans) - min(pl.nwin for pl in plans) <= 1
+    with pytest.raises(fa.FaError):
+        fa.windowed_slab_plan((16, 16), 5, 1, 2, 0, 2)      # overlapping windows: needs a halo reduce, not built
+
+
+def _slab_of(t, pl):
+    sl = [slice(None)] * t.ndim
+    sl[t.ndim - 3] = slice(pl[0], pl[1])
+    return np.asfortranarray(t[tuple(sl)])
+
+
+def test_oracle_slabs_assemble_to_whole_volume():
+    for spatial, W, stride, pad, G in (((12, 13), 5, 5, 2, 3), ((9, 31), 4, 6, 3, 2), ((6, 5, 14), 3, 3, 1, 3), ((10,), 5, 5, 2, 2)):
+        q, k, v = (randn_np(spatial + (4, 2), s).astype(np.float64) for s in range(3))
+        y0, l0, m0 = fo.windowed_fa(q, k, v, W, stride=stride, pad=pad)
+        parts = []
+        for r in range(G):
+            pl = fo.windowed_slab_plan(spatial, W, stride, pad, r, G)
+            if pl[3] > pl[2]:
+                parts.append(fo.windowed_fa_slab(*(_slab_of(t, pl) for t in (q, k, v)), W, stride, pad, pl[4], pl[3] - pl[2]))
+        y = np.concatenate([p[0] for p in parts], axis=len(spatial) - 1)
+        l = np.concatenate([p[1] for p in parts], axis=2)
+        m = np.concatenate([p[2] for p in parts], axis=2)
+        assert np.array_equal(np.isnan(y), np.isnan(y0)) and np.nanmax(np.abs(y - y0)) == 0
+        assert np.array_equal(l, l0) and np.array_equal(m, m0)
+
+
+def _gloo_slab_worker(rank, world, port, q, k, v, geo, out):
+    """Each rank works on its own slab only; nothing but the final gather crosses ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "flashattention.jl_b200"))
+    import fa_sm100a as fa
+    spatial, W, stride, pad = geo
+    pl = fa.windowed_slab_plan(spatial, W, stride, pad, rank, world)
+    y, l, m = fo.windowed_fa_slab(*(_slab_of(t, pl) for t in (q, k, v)), W, stride, pad, pl.pad_lo, pl.nwin)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (tuple(pl), np.ascontiguousarray(y), np.ascontiguousarray(l), np.ascontiguousarray(m)))
+    if rank == 0:
+        out["res"] = gathered
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_windowed_slabs_gloo_world2():
+    geo = ((8, 6, 12), 3, 3, 1)
+    spatial, W, stride, pad = geo
+    q, k, v = (randn_np(spatial + (4, 1), s).astype(np.float64) for s in range(3))
+    y0, l0, m0 = fo.windowed_fa(q, k, v, W, stride=stride, pad=pad)
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gloo_slab_worker, args=(world, port, q, k, v, geo, out), nprocs=world, join=True)
+    res = sorted(out["res"], key=lambda t: t[0][2])
+    y = np.concatenate([r[1] for r in res], axis=2)
+    l = np.concatenate([r[2] for r in res], axis=2)
+    assert np.array_equal(np.isnan(y), np.isnan(y0)) and np.nanmax(np.abs(y - y0)) == 0 and np.array_equal(l, l0)
 
 
 # ------------------------------------------------------------------------------------------- GPU
@@ -194,3 +274,37 @@ def test_ring_backward_nccl(dtype, world):
     tol = 1e-5 if dtype == torch.float32 else 2e-3
     for i, w in zip((3, 4, 5), want):
         assert rel_err(cat(i), w, dtype) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spatial,W,stride,pad,G,d,dtype", [
+    ((64, 64, 64), 5, 5, 3, 8, 64, torch.bfloat16),        # BASELINE config 5, single volume over 8 ranks
+    ((64, 64), 7, 7, 3, 3, 64, torch.bfloat16),            # config 2 geometry
+    ((20, 9), 3, 4, 1, 3, 32, torch.float32),              # gaps between windows: uncovered planes stay NaN
+    ((16,), 4, 4, 0, 2, 128, torch.float16),
+    ((7, 8, 30), 3, 3, 1, 4, 16, torch.float32),
+])
+def test_windowed_slabs_reproduce_whole_volume_bitwise(spatial, W, stride, pad, G, d, dtype):
+    """SURVEY 8(e), one volume over G ranks: every rank's slab (computed here one after the other on one GPU)
+    holds exactly the planes / windows of the one-GPU call, forward and backward, bit for bit."""
+    import fa_sm100a as fa
+    B = 1
+    q, k, v, g = (to_dev(randn_np(spatial + (d, B), s, dtype), dtype) for s in range(4))
+    y0, l0, m0 = fa.windowed_fa(q, k, v, W, stride=stride, pad=pad)
+    g0 = fa.windowed_fa_backward(q, k, v, g, l0, m0, W, stride=stride, pad=pad)
+    ax = len(spatial) - 1
+    ys, ls, ms, gs = [], [], [], ([], [], [])
+    for r in range(G):
+        pl = fa.windowed_slab_plan(spatial, W, stride, pad, r, G)
+        if pl.nwin == 0:
+            continue
+        qs, ks, vs, dys = (fa.slab_planes(t, pl) for t in (q, k, v, g))
+        y, l, m = fa.windowed_fa_slab(qs, ks, vs, W, pl, stride=stride, pad=pad)
+        grads = fa.windowed_fa_slab_backward(qs, ks, vs, dys, l, m, W, pl, stride=stride, pad=pad)
+        ys.append(y); ls.append(l); ms.append(m)
+        for acc, t in zip(gs, grads):
+            acc.append(t)
+    eq = lambda a, b: torch.equal(torch.nan_to_num(a.float(), nan=12345.0), torch.nan_to_num(b.float(), nan=12345.0))
+    assert eq(torch.cat(ys, dim=ax), y0) and eq(torch.cat(ls, dim=2), l0) and eq(torch.cat(ms, dim=2), m0)
+    for acc, want in zip(gs, g0):
+        assert eq(torch.cat(acc, dim=ax), want)
