@@ -1033,6 +1033,21 @@ int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   if (!tc_win_supported(g, dtype)) { set_error("tc_win_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
   const int fmt = dtype == FA_BF16 ? 1 : 0;
   if (g.d == 128) return fmt ? launch_win_fwd<128, 1, 1>(g, a, st) : launch_win_fwd<128, 1, 0>(g, a, st);
+  // d = 64: two 128-row tiles per CTA (2 CTAs / SM; longer x-runs per gather) or one tile per CTA (3 CTAs / SM).
+  // Small problems -- fewer than two pair-groups per resident CTA -- are latency bound and take the finer split
+  // (config 2: 19.0 -> 15.0 us); large ones keep the pair kernel (config 5: 0.93 vs 0.99 ms).  FA_WIN_NT overrides.
+  static const int nt_env = [] { const char* e = getenv("FA_WIN_NT"); return e ? atoi(e) : 0; }();
+  int nt = nt_env;
+  if (nt != 1 && nt != 2) {
+    WinMap mp2;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    make_map(g, 2, mp2);
+    const long long groups2 = (g.L * g.B + mp2.nwc - 1) / mp2.nwc;
+    nt = groups2 < 4LL * sms ? 1 : 2;
+  }
+  if (nt == 1) return fmt ? launch_win_fwd<64, 1, 1>(g, a, st) : launch_win_fwd<64, 1, 0>(g, a, st);
   return fmt ? launch_win_fwd<64, 2, 1>(g, a, st) : launch_win_fwd<64, 2, 0>(g, a, st);
 }
 
