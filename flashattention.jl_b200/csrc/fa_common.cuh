@@ -141,6 +141,8 @@ int softmax_launch(void* out, const void* in, long long M, long long N, long lon
 // tensor-core (tcgen05) forward: dense + circulant, 16-bit dtypes, d == dv in {64,128}
 bool tc_fwd_supported(const Geo& g, int dtype);
 int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
+// compact three-CTAs-per-SM forward for short key loops (circulant, d = dv = 64); dispatched from tc_fwd
+int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
 // tensor-core backward (two deterministic kernels: key-owner dK/dV, query-owner dQ); same coverage
 bool tc_bwd_supported(const Geo& g, int dtype);
 size_t tc_bwd_workspace_bytes(const Geo& g, int dtype, int flags);

@@ -1,0 +1,313 @@
+// fa_tc_band.cu -- compact tcgen05 / TMEM / TMA forward for SHORT key loops: circulant_fa! (reference
+// src/circulant.jl:9-118) with d == dv == 64, where a 128-query tile meets only (128 + W) / 64 key tiles.
+//
+// Why a second forward kernel: the pair kernel of fa_tc_fwd.cu is built for long key loops (S double
+// buffered, QK two steps ahead, 200-register softmax threads) and fits 2 CTAs = 2 query tiles per SM.  With
+// 6-7 key tiles per query tile the time goes to latencies -- prologue (barrier init, TMEM alloc, first TMA
+// round trip), mbarrier wake-ups between the roles, epilogue -- and not to any pipe (ncu, config 4: tensor
+// 16 %, MUFU 27 %, issue 40 %: profiles/r1s_ncu_summary.md).  The cure is more query tiles in flight per SM,
+// so this kernel is sized for THREE CTAs per SM:
+//   * one S buffer (64 TMEM columns; P aliases its first 32) + O (64 columns) = 128 columns per CTA;
+//   * 3-deep K and V rings + the Q tile = 64 KB of shared memory per CTA;
+//   * 256 threads at 80 launch registers: warps 0-3 (TMA producer, MMA issuer, TMEM allocator, idle) drop to 40,
+//     the four softmax warps (thread == query row) rise to 120 -- 128 x 40 + 128 x 120 = 256 x 80.
+// Per step the CTA is serial (QK(j) -> softmax(j) -> PV(j) -> QK(j+1)); the other two CTAs fill the gaps.
+// Layout, descriptors and masking are those of fa_tc_fwd.cu (token-contiguous [B][d][N], SWIZZLE_128B boxes of
+// 64 tokens x 64 channels, MN-major Q/K for S = Q K^T, K-major V for O = P V).
+#include <cuda.h>
+#include <stdlib.h>
+#include "fa_common.cuh"
+#include "fa_ptx.cuh"
+
+namespace fa {
+
+int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B);
+
+namespace {
+
+using namespace ptx;
+
+constexpr int BN = 64, D = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float RESCALE_THRESHOLD = 8.0f;
+
+struct BandCfg {
+  static constexpr int THREADS = 256, CTAS_PER_SM = 3;
+  static constexpr int STAGES = 3;
+  static constexpr int BOX_BYTES = 64 * D * 2, QTILE_BYTES = 2 * BOX_BYTES;
+  static constexpr int OFF_Q = 0, OFF_K = QTILE_BYTES, OFF_V = OFF_K + STAGES * BOX_BYTES, OFF_BAR = OFF_V + STAGES * BOX_BYTES;
+  static constexpr int BAR_QFULL = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + STAGES, BAR_VFULL = BAR_KEMPTY + STAGES,
+                       BAR_VEMPTY = BAR_VFULL + STAGES, BAR_SFULL = BAR_VEMPTY + STAGES, BAR_PFULL = BAR_SFULL + 1,
+                       BAR_OFINAL = BAR_PFULL + 1, NUM_BARS = BAR_OFINAL + 1;
+  static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;
+  static constexpr int TMEM_COLS = 128, COL_S = 0, COL_O = 64;
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "three CTAs per SM");
+};
+
+struct BandParams {
+  void* o;
+  float *l, *m;
+  int N, W, p;
+  float scale_log2;
+};
+
+__host__ __device__ inline int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if (FMT == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(BandCfg::THREADS, BandCfg::CTAS_PER_SM)
+tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+               const __grid_constant__ CUtensorMap tmv, const BandParams prm) {
+  using C = BandCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = sbase + C::OFF_Q, sK = sbase + C::OFF_K, sV = sbase + C::OFF_V;
+  auto bar = [&](int i) { return sbase + C::OFF_BAR + 8u * (uint32_t)i; };
+  const uint32_t tmem_slot = sbase + C::OFF_TMEM_SLOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, b = blockIdx.y;
+
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar(C::BAR_QFULL), 1);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), 1);
+      mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), 1);
+    }
+    mbar_init(bar(C::BAR_SFULL), 1); mbar_init(bar(C::BAR_PFULL), 128); mbar_init(bar(C::BAR_OFINAL), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // key tiles of this query tile: keys (q - p) .. (q - p + W - 1) for q in [q0, q0 + 128), from the 64-aligned
+  // tile at or below q0 - p (src/circulant.jl:61-67: the window of query j starts p keys before it, periodic)
+  const int kbase = fdiv(q0 - prm.p, BN) * BN;
+  const int nj = fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      mbar_arrive_expect_tx(bar(C::BAR_QFULL), C::QTILE_BYTES);
+      tma_load_3d(sQ, &tmq, bar(C::BAR_QFULL), q0, 0, b);
+      tma_load_3d(sQ + C::BOX_BYTES, &tmq, bar(C::BAR_QFULL), q0 + 64, 0, b);
+      for (int j = 0; j < nj; ++j) {
+        const int s = j % C::STAGES;
+        const uint32_t par = ((uint32_t)(j / C::STAGES) & 1u) ^ 1u;
+        const int tok = (int)pmod(kbase + BN * j, prm.N);
+        mbar_wait(bar(C::BAR_KEMPTY + s), par);
+        mbar_arrive_expect_tx(bar(C::BAR_KFULL + s), C::BOX_BYTES);
+        tma_load_3d(sK + s * C::BOX_BYTES, &tmk, bar(C::BAR_KFULL + s), tok, 0, b);
+        mbar_wait(bar(C::BAR_VEMPTY + s), par);
+        mbar_arrive_expect_tx(bar(C::BAR_VFULL + s), C::BOX_BYTES);
+        tma_load_3d(sV + s * C::BOX_BYTES, &tmv, bar(C::BAR_VFULL + s), tok, 0, b);
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+      constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, BN);
+      constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);
+      const uint64_t qdesc = make_smem_desc_sw128(sQ, C::BOX_BYTES, 1024);
+      const uint64_t kdesc = make_smem_desc_sw128(sK, C::BOX_BYTES, 1024);
+      const uint64_t vdesc = make_smem_desc_sw128(sV, 16, 1024);
+      const uint32_t tS = tmem_base + C::COL_S, tO = tmem_base + C::COL_O;
+      mbar_wait(bar(C::BAR_QFULL), 0);
+      for (int j = 0; j < nj; ++j) {
+        const int s = j % C::STAGES;
+        const uint32_t par = (uint32_t)(j / C::STAGES) & 1u;
+        // S = Q K(j)^T.  PV(j-1), which read P out of this buffer, was issued before: the tensor pipe runs in order.
+        mbar_wait(bar(C::BAR_KFULL + s), par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t kd = kdesc + (uint64_t)(s * (C::BOX_BYTES >> 4));
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tS, qdesc + (uint64_t)(ks * 128), kd + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
+          tc_commit(bar(C::BAR_SFULL));          // also: every earlier MMA (PV(j-1)) has completed
+          tc_commit(bar(C::BAR_KEMPTY + s));
+        }
+        __syncwarp();
+        // O += P(j) V(j)
+        mbar_wait(bar(C::BAR_VFULL + s), par);
+        mbar_wait(bar(C::BAR_PFULL), (uint32_t)j & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = vdesc + (uint64_t)(s * (C::BOX_BYTES >> 4));
+#pragma unroll
+          for (int ks = 0; ks < BN / 16; ++ks)
+            mma_ts(tO, tS + ks * 8, vd + (uint64_t)(ks * 2), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          tc_commit(bar(C::BAR_VEMPTY + s));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(bar(C::BAR_OFINAL));
+      __syncwarp();
+    }
+  } else {
+    // -------------------------------------------------------------- softmax: thread == query row
+    setmaxnreg_inc<120>();
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + C::COL_S, tO = tmem_base + lane_addr + C::COL_O;
+    const int qi = q0 + row;
+    const float scale = prm.scale_log2;
+    const float2 scale2 = make_float2(scale, scale);
+    float m_true = -INFINITY, m_used = -INFINITY;
+    float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
+    const int lo0 = (qi - prm.p) - kbase;                       // first in-band column of key tile 0 for this row
+
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) {
+      const int lo = lo0 - BN * j, hi = lo + prm.W;            // lo <= col < hi stays
+      mbar_wait(bar(C::BAR_SFULL), (uint32_t)j & 1u);
+      tc_fence_after();
+      // a key tile outside the band of every row of this warp contributes P = 0 (warp-uniform)
+      if (__all_sync(0xffffffffu, hi <= 0 || lo >= BN)) {
+        uint32_t z[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z[e] = 0u;
+        tmem_st16(tS, z);
+        tmem_st16(tS + 16, z);
+      } else {
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS, s0);
+        tmem_ld32(tS + 32, s1);
+        tmem_wait_ld();
+        if (lo > 0 || hi < BN) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e < lo || e >= hi) s0[e] = 0xff800000u;
+            if (e + 32 < lo || e + 32 >= hi) s1[e] = 0xff800000u;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[e]), __uint_as_float(s0[e + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1])));
+        }
+        m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
+        // lazy rescale (warp-uniform decision).  S(j) complete implies PV(j-1) complete: O may be touched.
+        const bool want = (m_true - m_used) > RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, want)) {
+          const float alpha = (m_used == -INFINITY) ? 0.f : ex2(m_used - m_true);
+          if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < D / 16; ++c) {
+              uint32_t o[16];
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                  : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]),
+                    "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+                  : "r"(tO + 16 * c) : "memory");
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st16(tO + 16 * c, o);
+            }
+          }
+          l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
+          m_used = m_true;
+        }
+        const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+        const float2 negm2 = make_float2(neg_m, neg_m);
+        // P = exp2(s * scale - m) -> 16 bit, over the first 32 columns of S (blocks of 8: 4 FFMA2, 8 ex2, 4 FADD2 + 4 packs)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+          const uint32_t(&sc)[32] = c == 0 ? s0 : s1;
+#pragma unroll
+          for (int e0 = 0; e0 < 32; e0 += 8) {
+            float2 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              x[u] = __ffma2_rn(make_float2(__uint_as_float(sc[e0 + 2 * u]), __uint_as_float(sc[e0 + 2 * u + 1])), scale2, negm2);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { x[u].x = ex2(x[u].x); x[u].y = ex2(x[u].y); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (u & 1) l2b = __fadd2_rn(l2b, x[u]); else l2a = __fadd2_rn(l2a, x[u]);
+              pk[(e0 >> 1) + u] = pack16<FMT>(x[u].x, x[u].y);
+            }
+          }
+          tmem_st16(tS + 16 * c, pk);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar(C::BAR_PFULL));
+    }
+    const float l_run = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+
+    // ---- epilogue: O / l -> global (token-contiguous rows: a warp writes 32 consecutive tokens per channel)
+    mbar_wait(bar(C::BAR_OFINAL), 0);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const bool in_range = qi < prm.N;
+    unsigned short* ob = static_cast<unsigned short*>(prm.o) + (size_t)b * D * prm.N + qi;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + 32 * c, o);
+      tmem_wait_ld();
+      if (in_range) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const uint32_t pr = pack16<FMT>(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l);
+          ob[(size_t)(32 * c + e) * prm.N] = (unsigned short)(pr & 0xffffu);
+          ob[(size_t)(32 * c + e + 1) * prm.N] = (unsigned short)(pr >> 16);
+        }
+      }
+    }
+    if (in_range) {
+      // l = sum exp(s - m_true), m = max s (natural-log domain), reference src/circulant.jl:110-116
+      prm.l[(size_t)b * prm.N + qi] = l_run * ex2(m_used - m_true);
+      prm.m[(size_t)b * prm.N + qi] = m_true * LN2;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int FMT>
+int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
+  using C = BandCfg;
+  CUtensorMap tmq, tmk, tmv;
+  int rc;
+  if ((rc = make_tmap_public(&tmq, a.q, dtype, g.N, D, g.B))) return rc;
+  if ((rc = make_tmap_public(&tmk, a.k, dtype, g.N, D, g.B))) return rc;
+  if ((rc = make_tmap_public(&tmv, a.v, dtype, g.N, D, g.B))) return rc;
+  BandParams prm;
+  prm.o = a.o; prm.l = a.l; prm.m = a.m;
+  prm.N = (int)g.N; prm.W = g.W; prm.p = g.p;
+  prm.scale_log2 = g.tau * LOG2E;
+  auto kern = tc_band_kernel<FMT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.B);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+}  // namespace
+
+// circulant, d = dv = 64, 16-bit output, tile-aligned wrap-around (N % 64 == 0) -- checked by the caller (tc_fwd)
+int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
+  return dtype == FA_BF16 ? launch_band<1>(g, a, dtype, st) : launch_band<0>(g, a, dtype, st);
+}
+
+}  // namespace fa

@@ -908,6 +908,9 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   // short key loops (circulant with a band of a few tiles): one Q tile per CTA, two CTAs per SM
   const bool short_loop = g.mode == MODE_CIRCULANT && (256 + g.W) / 64 <= 24;
   if (short_loop) {
+    // d = 64: the compact band kernel (three CTAs per SM, fa_tc_band.cu); FA_BAND=0 keeps the two-CTA variant below
+    static const int band = [] { const char* e = getenv("FA_BAND"); return e ? atoi(e) : 1; }();
+    if (band && g.d == 64 && !a.o_f32) return tc_band_fwd(g, a, dtype, st);
     if (g.d == 128) return fmt ? launch_tc<128, 1, 1>(g, a, dtype, st) : launch_tc<128, 0, 1>(g, a, dtype, st);
     return fmt ? launch_tc<64, 1, 1>(g, a, dtype, st) : launch_tc<64, 0, 1>(g, a, dtype, st);
   }
