@@ -6,11 +6,16 @@
 // 6-7 key tiles per query tile the time goes to latencies -- prologue (barrier init, TMEM alloc, first TMA
 // round trip), mbarrier wake-ups between the roles, epilogue -- and not to any pipe (ncu, config 4: tensor
 // 16 %, MUFU 27 %, issue 40 %: profiles/r1s_ncu_summary.md).  The cure is more query tiles in flight per SM,
-// so this kernel is sized for THREE CTAs per SM:
+// so this kernel is sized for FOUR (FA_BAND_CTAS=3: three) CTAs per SM:
 //   * one S buffer (64 TMEM columns; P aliases its first 32) + O (64 columns) = 128 columns per CTA;
-//   * 3-deep K and V rings + the Q tile = 64 KB of shared memory per CTA;
-//   * 256 threads at 80 launch registers: warps 0-3 (TMA producer, MMA issuer, TMEM allocator, idle) drop to 40,
-//     the four softmax warps (thread == query row) rise to 120 -- 128 x 40 + 128 x 120 = 256 x 80.
+//   * 2-deep (3-deep) K and V rings + the Q tile = 48 (64) KB of shared memory per CTA;
+//   * 256 threads at 64 (80) launch registers: warps 0-3 (TMA producer, MMA issuer, TMEM allocator, idle) drop to
+//     32 (40), the four softmax warps (thread == query row) rise to 96 (120).  At 96 registers a softmax thread
+//     holds one 32-column chunk of its S row at a time and reads S twice (row max, then exponentials).
+//   * each 32-column chunk is classified per warp against the band (inside / outside / mixed): only mixed chunks
+//     pay the per-element select, chunks outside the band of all 32 rows are neither read nor exponentiated.
+// Measured at config 4 (N = 16384, W = 255, B = 512, bf16; same box): two-CTA pair kernel 2.317 ms, this kernel
+// with three CTAs 1.811 ms, with four 1.645 ms (profiles/r1t_band_kernel.md).
 // Per step the CTA is serial (QK(j) -> softmax(j) -> PV(j) -> QK(j+1)); the other two CTAs fill the gaps.
 // Layout, descriptors and masking are those of fa_tc_fwd.cu (token-contiguous [B][d][N], SWIZZLE_128B boxes of
 // 64 tokens x 64 channels, MN-major Q/K for S = Q K^T, K-major V for O = P V).
@@ -32,9 +37,9 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
-struct BandCfg {
-  static constexpr int THREADS = 256, CTAS_PER_SM = 3;
-  static constexpr int STAGES = 3;
+template <int CTAS> struct BandCfg {
+  static constexpr int THREADS = 256, CTAS_PER_SM = CTAS;
+  static constexpr int STAGES = CTAS == 4 ? 2 : 3;
   static constexpr int BOX_BYTES = 64 * D * 2, QTILE_BYTES = 2 * BOX_BYTES;
   static constexpr int OFF_Q = 0, OFF_K = QTILE_BYTES, OFF_V = OFF_K + STAGES * BOX_BYTES, OFF_BAR = OFF_V + STAGES * BOX_BYTES;
   static constexpr int BAR_QFULL = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + STAGES, BAR_VFULL = BAR_KEMPTY + STAGES,
@@ -43,7 +48,8 @@ struct BandCfg {
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;
   static constexpr int TMEM_COLS = 128, COL_S = 0, COL_O = 64;
-  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "three CTAs per SM");
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory for CTAS CTAs per SM");
+  static_assert(CTAS_PER_SM * TMEM_COLS <= 512, "TMEM");
 };
 
 struct BandParams {
@@ -51,7 +57,19 @@ struct BandParams {
   float *l, *m;
   int N, W, p;
   float scale_log2;
+  long long* trace;      // FA_TRACE builds: one CTA in the middle of the grid records clock64() per event
 };
+
+#ifdef FA_TRACE
+// slot = role * 128 + step * 8 + event; role 0 = issuer, 1 = softmax warp 4; step 15 = per-CTA events
+#define BTRACE(role, step, ev)                                                                              \
+  do {                                                                                                      \
+    if (prm.trace && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 && lane == 0 && (step) < 16) \
+      prm.trace[(role) * 128 + (step) * 8 + (ev)] = clock64();                                               \
+  } while (0)
+#else
+#define BTRACE(role, step, ev) do {} while (0)
+#endif
 
 __host__ __device__ inline int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -62,11 +80,12 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(BandCfg::THREADS, BandCfg::CTAS_PER_SM)
+template <int FMT, int CTAS>
+__global__ void __launch_bounds__(BandCfg<CTAS>::THREADS, BandCfg<CTAS>::CTAS_PER_SM)
 tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                const __grid_constant__ CUtensorMap tmv, const BandParams prm) {
-  using C = BandCfg;
+  using C = BandCfg<CTAS>;
+  constexpr bool TWO_PASS = CTAS == 4;   // 96-register softmax threads hold one 32-column chunk at a time
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase + C::OFF_Q, sK = sbase + C::OFF_K, sV = sbase + C::OFF_V;
@@ -74,6 +93,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   const uint32_t tmem_slot = sbase + C::OFF_TMEM_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, b = blockIdx.y;
+  if (warp == 1) BTRACE(0, 15, 0);                         // kernel entry
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv); }
   if (warp == 1 && lane == 0) {
@@ -91,6 +111,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 1) BTRACE(0, 15, 1);                         // set-up done
 
   // key tiles of this query tile: keys (q - p) .. (q - p + W - 1) for q in [q0, q0 + 128), from the 64-aligned
   // tile at or below q0 - p (src/circulant.jl:61-67: the window of query j starts p keys before it, periodic)
@@ -98,7 +119,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   const int nj = fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1;
 
   if (warp < 4) {
-    setmaxnreg_dec<40>();
+    if (CTAS == 4) setmaxnreg_dec<32>(); else setmaxnreg_dec<40>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
       mbar_arrive_expect_tx(bar(C::BAR_QFULL), C::QTILE_BYTES);
@@ -124,11 +145,13 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       const uint64_t vdesc = make_smem_desc_sw128(sV, 16, 1024);
       const uint32_t tS = tmem_base + C::COL_S, tO = tmem_base + C::COL_O;
       mbar_wait(bar(C::BAR_QFULL), 0);
+      BTRACE(0, 15, 2);                                     // Q landed
       for (int j = 0; j < nj; ++j) {
         const int s = j % C::STAGES;
         const uint32_t par = (uint32_t)(j / C::STAGES) & 1u;
         // S = Q K(j)^T.  PV(j-1), which read P out of this buffer, was issued before: the tensor pipe runs in order.
         mbar_wait(bar(C::BAR_KFULL + s), par);
+        BTRACE(0, j, 0);                                    // K(j) ready
         tc_fence_after();
         if (elect_one()) {
           const uint64_t kd = kdesc + (uint64_t)(s * (C::BOX_BYTES >> 4));
@@ -139,9 +162,11 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           tc_commit(bar(C::BAR_KEMPTY + s));
         }
         __syncwarp();
+        BTRACE(0, j, 1);                                    // QK(j) issued
         // O += P(j) V(j)
         mbar_wait(bar(C::BAR_VFULL + s), par);
         mbar_wait(bar(C::BAR_PFULL), (uint32_t)j & 1u);
+        BTRACE(0, j, 2);                                    // P(j) seen
         tc_fence_after();
         if (elect_one()) {
           const uint64_t vd = vdesc + (uint64_t)(s * (C::BOX_BYTES >> 4));
@@ -151,13 +176,14 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           tc_commit(bar(C::BAR_VEMPTY + s));
         }
         __syncwarp();
+        BTRACE(0, j, 3);                                    // PV(j) issued
       }
       if (elect_one()) tc_commit(bar(C::BAR_OFINAL));
       __syncwarp();
     }
   } else {
     // -------------------------------------------------------------- softmax: thread == query row
-    setmaxnreg_inc<120>();
+    if (CTAS == 4) setmaxnreg_inc<96>(); else setmaxnreg_inc<120>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + C::COL_S, tO = tmem_base + lane_addr + C::COL_O;
@@ -168,37 +194,97 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
     const int lo0 = (qi - prm.p) - kbase;                       // first in-band column of key tile 0 for this row
 
+    // x16 TMEM load (rescale of O in 16-column pieces keeps the register peak low)
+    auto tmem_ld16 = [](uint32_t taddr, uint32_t (&o)[16]) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]),
+            "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+          : "r"(taddr) : "memory");
+    };
+    // mask of one 32-column chunk held in registers: columns outside [lo, hi) (chunk-relative) become -inf
+    auto mask32 = [](uint32_t (&sc)[32], int lo, int hi) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < lo || e >= hi) sc[e] = 0xff800000u;
+    };
+    auto max32 = [](const uint32_t (&sc)[32]) {
+      float a = -INFINITY, bq = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        a = fmaxf(a, fmaxf(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])));
+        bq = fmaxf(bq, fmaxf(__uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3])));
+      }
+      return fmaxf(a, bq);
+    };
+    // P chunk = exp2(s * scale - m) -> 16 bit (blocks of 8: 4 FFMA2, 8 ex2, 4 FADD2 + 4 packs), stored over S
+    auto exp32 = [&](const uint32_t (&sc)[32], float2 negm2, uint32_t dst) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int e0 = 0; e0 < 32; e0 += 8) {
+        float2 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          x[u] = __ffma2_rn(make_float2(__uint_as_float(sc[e0 + 2 * u]), __uint_as_float(sc[e0 + 2 * u + 1])), scale2, negm2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u].x = ex2(x[u].x); x[u].y = ex2(x[u].y); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u & 1) l2b = __fadd2_rn(l2b, x[u]); else l2a = __fadd2_rn(l2a, x[u]);
+          pk[(e0 >> 1) + u] = pack16<FMT>(x[u].x, x[u].y);
+        }
+      }
+      tmem_st16(dst, pk);
+    };
+    auto zero16 = [](uint32_t dst) {
+      uint32_t z[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) z[e] = 0u;
+      tmem_st16(dst, z);
+    };
+
 #pragma unroll 1
     for (int j = 0; j < nj; ++j) {
       const int lo = lo0 - BN * j, hi = lo + prm.W;            // lo <= col < hi stays
+      // Each 32-column chunk is classified per warp (the band edge is a diagonal: it crosses ~32 columns over a
+      // warp's 32 rows): 1 = inside the band of every lane (no predicates), 2 = outside for every lane (P = 0: S is
+      // not read, no exponentials), 0 = mixed (per-element select).
+      uint32_t kc[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const bool in = lo <= 32 * c && 32 * c + 32 <= hi, out = hi <= 32 * c || lo >= 32 * c + 32;
+        kc[c] = __all_sync(0xffffffffu, in) ? 1u : (__all_sync(0xffffffffu, out) ? 2u : 0u);
+      }
       mbar_wait(bar(C::BAR_SFULL), (uint32_t)j & 1u);
+      if (warp == 4) BTRACE(1, j, 0);                       // S(j) seen
       tc_fence_after();
-      // a key tile outside the band of every row of this warp contributes P = 0 (warp-uniform)
-      if (__all_sync(0xffffffffu, hi <= 0 || lo >= BN)) {
-        uint32_t z[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) z[e] = 0u;
-        tmem_st16(tS, z);
-        tmem_st16(tS + 16, z);
+      if (kc[0] == 2u && kc[1] == 2u) {
+        zero16(tS); zero16(tS + 16);
       } else {
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tS, s0);
-        tmem_ld32(tS + 32, s1);
-        tmem_wait_ld();
-        if (lo > 0 || hi < BN) {
+        uint32_t s0[32], s1[TWO_PASS ? 1 : 32];
+        float mx = -INFINITY;
+        if (TWO_PASS) {
+          // ---- pass 1: row max, one chunk in registers at a time
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (e < lo || e >= hi) s0[e] = 0xff800000u;
-            if (e + 32 < lo || e + 32 >= hi) s1[e] = 0xff800000u;
+          for (int c = 0; c < 2; ++c) {
+            if (kc[c] != 2u) {
+              tmem_ld32(tS + 32 * c, s0);
+              tmem_wait_ld();
+              if (kc[c] == 0u) mask32(s0, lo - 32 * c, hi - 32 * c);
+              mx = fmaxf(mx, max32(s0));
+            }
           }
+        } else {
+          if (kc[0] != 2u) tmem_ld32(tS, s0);
+          if (kc[1] != 2u) tmem_ld32(tS + 32, (uint32_t(&)[32])s1);
+          tmem_wait_ld();
+          if (kc[0] == 0u) mask32(s0, lo, hi);
+          if (kc[1] == 0u) mask32((uint32_t(&)[32])s1, lo - 32, hi - 32);
+          if (kc[0] != 2u) mx = max32(s0);
+          if (kc[1] != 2u) mx = fmaxf(mx, max32((uint32_t(&)[32])s1));
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[e]), __uint_as_float(s0[e + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1])));
-        }
-        m_true = fmaxf(m_true, fmaxf(mx0, mx1) * scale);
+        m_true = fmaxf(m_true, mx * scale);
+        if (warp == 4) BTRACE(1, j, 1);                     // max done
         // lazy rescale (warp-uniform decision).  S(j) complete implies PV(j-1) complete: O may be touched.
         const bool want = (m_true - m_used) > RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, want)) {
@@ -207,11 +293,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 #pragma unroll 1
             for (int c = 0; c < D / 16; ++c) {
               uint32_t o[16];
-              asm volatile(
-                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                  : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]),
-                    "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
-                  : "r"(tO + 16 * c) : "memory");
+              tmem_ld16(tO + 16 * c, o);
               tmem_wait_ld();
 #pragma unroll
               for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
@@ -221,38 +303,36 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           l2a.x *= alpha; l2a.y *= alpha; l2b.x *= alpha; l2b.y *= alpha;
           m_used = m_true;
         }
+        if (warp == 4) BTRACE(1, j, 2);                     // rescale decided / done
         const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
         const float2 negm2 = make_float2(neg_m, neg_m);
-        // P = exp2(s * scale - m) -> 16 bit, over the first 32 columns of S (blocks of 8: 4 FFMA2, 8 ex2, 4 FADD2 + 4 packs)
+        // ---- P over the first 32 columns of S.  Chunk 0 is in registers before its own columns are overwritten,
+        // chunk 1 (columns 32-63) is read before P lands in columns 16-31.
+        if (TWO_PASS) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-          const uint32_t(&sc)[32] = c == 0 ? s0 : s1;
-#pragma unroll
-          for (int e0 = 0; e0 < 32; e0 += 8) {
-            float2 x[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              x[u] = __ffma2_rn(make_float2(__uint_as_float(sc[e0 + 2 * u]), __uint_as_float(sc[e0 + 2 * u + 1])), scale2, negm2);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { x[u].x = ex2(x[u].x); x[u].y = ex2(x[u].y); }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (u & 1) l2b = __fadd2_rn(l2b, x[u]); else l2a = __fadd2_rn(l2a, x[u]);
-              pk[(e0 >> 1) + u] = pack16<FMT>(x[u].x, x[u].y);
-            }
+          for (int c = 0; c < 2; ++c) {
+            if (kc[c] == 2u) { zero16(tS + 16 * c); continue; }
+            tmem_ld32(tS + 32 * c, s0);
+            tmem_wait_ld();
+            if (kc[c] == 0u) mask32(s0, lo - 32 * c, hi - 32 * c);
+            exp32(s0, negm2, tS + 16 * c);
           }
-          tmem_st16(tS + 16 * c, pk);
+        } else {
+          if (kc[0] == 2u) zero16(tS); else exp32(s0, negm2, tS);
+          if (kc[1] == 2u) zero16(tS + 16); else exp32((uint32_t(&)[32])s1, negm2, tS + 16);
         }
       }
+      if (warp == 4) BTRACE(1, j, 3);                       // exps done, P stores issued
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar(C::BAR_PFULL));
+      if (warp == 4) BTRACE(1, j, 4);                       // P published
     }
     const float l_run = (l2a.x + l2a.y) + (l2b.x + l2b.y);
 
     // ---- epilogue: O / l -> global (token-contiguous rows: a warp writes 32 consecutive tokens per channel)
     mbar_wait(bar(C::BAR_OFINAL), 0);
+    if (warp == 4) BTRACE(1, 15, 0);                        // all MMAs done
     tc_fence_after();
     const float inv_l = 1.f / l_run;
     const bool in_range = qi < prm.N;
@@ -276,6 +356,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       prm.l[(size_t)b * prm.N + qi] = l_run * ex2(m_used - m_true);
       prm.m[(size_t)b * prm.N + qi] = m_true * LN2;
     }
+    if (warp == 4) BTRACE(1, 15, 1);                        // epilogue stores issued
   }
 
   tc_fence_before();
@@ -283,9 +364,9 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int FMT>
+template <int FMT, int CTAS>
 int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
-  using C = BandCfg;
+  using C = BandCfg<CTAS>;
   CUtensorMap tmq, tmk, tmv;
   int rc;
   if ((rc = make_tmap_public(&tmq, a.q, dtype, g.N, D, g.B))) return rc;
@@ -295,7 +376,11 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.W = g.W; prm.p = g.p;
   prm.scale_log2 = g.tau * LOG2E;
-  auto kern = tc_band_kernel<FMT>;
+  prm.trace = nullptr;
+#ifdef FA_TRACE
+  { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
+  auto kern = tc_band_kernel<FMT, CTAS>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.B);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
@@ -307,7 +392,9 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
 
 // circulant, d = dv = 64, 16-bit output, tile-aligned wrap-around (N % 64 == 0) -- checked by the caller (tc_fwd)
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
-  return dtype == FA_BF16 ? launch_band<1>(g, a, dtype, st) : launch_band<0>(g, a, dtype, st);
+  static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
+  if (ctas != 3) return dtype == FA_BF16 ? launch_band<1, 4>(g, a, dtype, st) : launch_band<0, 4>(g, a, dtype, st);
+  return dtype == FA_BF16 ? launch_band<1, 3>(g, a, dtype, st) : launch_band<0, 3>(g, a, dtype, st);
 }
 
 }  // namespace fa
