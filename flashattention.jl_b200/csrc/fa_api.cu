@@ -487,9 +487,14 @@ int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l
   if (device < 0 || device >= 16) { set_error("device index out of range"); return FA_ERR_INVALID; }
   const size_t esz = dtype_size(dtype);
   const size_t per_b = (2 * q_elems_per_b + 2 * v_elems_per_b) * esz + 2 * stat_per_b * 4;
+  // The pipeline is bound by the host->device copies (PCIe); what it adds on top is the tail -- kernel and
+  // device->host copy of the LAST chunk -- so big jobs are cut into ~16 chunks (16 MiB .. 256 MiB of tensors each).
   int64_t chunk = B;
-  const size_t target = (size_t)256 << 20;                 // ~256 MiB of tensors in flight per chunk
-  if (per_b * (size_t)B > 2 * target) { chunk = (int64_t)(target / per_b); if (chunk < 1) chunk = 1; }
+  const size_t total = per_b * (size_t)B;
+  size_t target = total / 16;
+  if (target < ((size_t)16 << 20)) target = (size_t)16 << 20;
+  if (target > ((size_t)256 << 20)) target = (size_t)256 << 20;
+  if (total > 2 * target) { chunk = (int64_t)(target / per_b); if (chunk < 1) chunk = 1; }
   const int nbuf = chunk < B ? 2 : 1;
   const size_t bq = align256(chunk * q_elems_per_b * esz), bv = align256(chunk * v_elems_per_b * esz), bs = align256(chunk * stat_per_b * 4);
   const size_t per_set = 2 * bq + 2 * bv + 2 * bs;
@@ -506,8 +511,18 @@ int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l
     dq[i].p = base; dk[i].p = base + bq; dvv[i].p = base + 2 * bq; dout[i].p = base + 2 * bq + bv;
     dl[i].p = base + 2 * bq + 2 * bv; dm[i].p = base + 2 * bq + 2 * bv + bs;
   }
-  cudaStream_t s[2];
-  cudaEvent_t done[2];
+  struct Lanes {           // two copy/compute lanes; released on every exit path
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    ~Lanes() {
+      for (int i = 0; i < 2; ++i) {
+        if (s[i]) { cudaStreamSynchronize(s[i]); cudaStreamDestroy(s[i]); }
+        if (done[i]) cudaEventDestroy(done[i]);
+      }
+    }
+  } lanes;
+  cudaStream_t* s = lanes.s;
+  cudaEvent_t* done = lanes.done;
   for (int i = 0; i < 2; ++i) { FA_CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)); FA_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); }
   int it = 0;
   for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
@@ -528,7 +543,6 @@ int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l
     FA_CUDA_TRY(cudaEventRecord(done[i], st));
   }
   for (int i = 0; i < 2; ++i) FA_CUDA_TRY(cudaStreamSynchronize(s[i]));
-  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(s[i]); cudaEventDestroy(done[i]); }
   return FA_OK;
 }
 }  // namespace
