@@ -67,9 +67,32 @@ struct BandParams {
     if (prm.trace && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 && lane == 0 && (step) < 16) \
       prm.trace[(role) * 128 + (step) * 8 + (ev)] = clock64();                                               \
   } while (0)
+#define BTRACE_E(role, step, ev)                                                                            \
+  do {                                                                                                      \
+    if (prm.trace && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2 && (step) < 16)              \
+      prm.trace[(role) * 128 + (step) * 8 + (ev)] = clock64();                                               \
+  } while (0)
 #else
 #define BTRACE(role, step, ev) do {} while (0)
+#define BTRACE_E(role, step, ev) do {} while (0)
 #endif
+
+// FA_BAND_SPIN: poll the two hand-off barriers of the per-step chain (S ready -> softmax, P ready -> issuer) with
+// the non-suspending test_wait instead of try_wait (which may park the thread for a system-dependent time)
+#ifndef FA_BAND_SPIN
+#define FA_BAND_SPIN 0
+#endif
+__device__ __forceinline__ void chain_wait(uint32_t bar, uint32_t parity) {
+#if FA_BAND_SPIN
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("fa_sm100a: band kernel hand-off timeout\n"); __trap(); }
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 
 __host__ __device__ inline int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -158,6 +181,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
             mma_ss(tS, qdesc + (uint64_t)(ks * 128), kd + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
+          BTRACE_E(0, j, 4);                                // QK MMAs handed to the pipe (elected lane)
           tc_commit(bar(C::BAR_SFULL));          // also: every earlier MMA (PV(j-1)) has completed
           tc_commit(bar(C::BAR_KEMPTY + s));
         }
@@ -165,7 +189,8 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         BTRACE(0, j, 1);                                    // QK(j) issued
         // O += P(j) V(j)
         mbar_wait(bar(C::BAR_VFULL + s), par);
-        mbar_wait(bar(C::BAR_PFULL), (uint32_t)j & 1u);
+        BTRACE(0, j, 5);                                    // V(j) ready
+        chain_wait(bar(C::BAR_PFULL), (uint32_t)j & 1u);
         BTRACE(0, j, 2);                                    // P(j) seen
         tc_fence_after();
         if (elect_one()) {
@@ -173,6 +198,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 #pragma unroll
           for (int ks = 0; ks < BN / 16; ++ks)
             mma_ts(tO, tS + ks * 8, vd + (uint64_t)(ks * 2), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+          BTRACE_E(0, j, 6);                                // PV MMAs handed to the pipe (elected lane)
           tc_commit(bar(C::BAR_VEMPTY + s));
         }
         __syncwarp();
@@ -203,10 +229,23 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           : "r"(taddr) : "memory");
     };
     // mask of one 32-column chunk held in registers: columns outside [lo, hi) (chunk-relative) become -inf
+    // (W >= 32 means a chunk meets at most one band edge for most warps: the one-sided forms save a compare per
+    // element; `side` is warp-uniform: 1 = left edge only, 2 = right edge only, 0 = both)
     auto mask32 = [](uint32_t (&sc)[32], int lo, int hi) {
+      const uint32_t side = __all_sync(0xffffffffu, hi >= 32) ? 1u : (__all_sync(0xffffffffu, lo <= 0) ? 2u : 0u);
+      if (side == 1u) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (e < lo || e >= hi) sc[e] = 0xff800000u;
+        for (int e = 0; e < 32; ++e)
+          if (e < lo) sc[e] = 0xff800000u;
+      } else if (side == 2u) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e >= hi) sc[e] = 0xff800000u;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < lo || e >= hi) sc[e] = 0xff800000u;
+      }
     };
     auto max32 = [](const uint32_t (&sc)[32]) {
       float a = -INFINITY, bq = -INFINITY;
@@ -255,7 +294,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         const bool in = lo <= 32 * c && 32 * c + 32 <= hi, out = hi <= 32 * c || lo >= 32 * c + 32;
         kc[c] = __all_sync(0xffffffffu, in) ? 1u : (__all_sync(0xffffffffu, out) ? 2u : 0u);
       }
-      mbar_wait(bar(C::BAR_SFULL), (uint32_t)j & 1u);
+      chain_wait(bar(C::BAR_SFULL), (uint32_t)j & 1u);
       if (warp == 4) BTRACE(1, j, 0);                       // S(j) seen
       tc_fence_after();
       if (kc[0] == 2u && kc[1] == 2u) {
@@ -270,10 +309,14 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
             if (kc[c] != 2u) {
               tmem_ld32(tS + 32 * c, s0);
               tmem_wait_ld();
-              if (kc[c] == 0u) mask32(s0, lo - 32 * c, hi - 32 * c);
+              if (kc[c] == 0u) {                    // masked once: pass 2 reads the masked chunk back
+                mask32(s0, lo - 32 * c, hi - 32 * c);
+                tmem_st32(tS + 32 * c, s0);
+              }
               mx = fmaxf(mx, max32(s0));
             }
           }
+          if (kc[0] == 0u || kc[1] == 0u) tmem_wait_st();
         } else {
           if (kc[0] != 2u) tmem_ld32(tS, s0);
           if (kc[1] != 2u) tmem_ld32(tS + 32, (uint32_t(&)[32])s1);
@@ -314,7 +357,6 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
             if (kc[c] == 2u) { zero16(tS + 16 * c); continue; }
             tmem_ld32(tS + 32 * c, s0);
             tmem_wait_ld();
-            if (kc[c] == 0u) mask32(s0, lo - 32 * c, hi - 32 * c);
             exp32(s0, negm2, tS + 16 * c);
           }
         } else {

@@ -20,10 +20,10 @@ base = int(t[0, 15, 0])
 rel = lambda x: int(x) - base if x > 0 else -1
 print("CTA: entry 0, set-up done", rel(t[0, 15, 1]), "Q landed", rel(t[0, 15, 2]), "all MMAs done", rel(t[1, 15, 0]),
       "epilogue stores issued", rel(t[1, 15, 1]))
-print("issuer  [K ready, QK issued, P seen, PV issued]")
+print("issuer  [K ready, QK issued (after commits), P seen, PV issued (after commit), QK MMAs handed over, V ready, PV MMAs handed over]")
 for j in range(8):
     if t[0, j, 0] > 0:
-        print("  step", j, [rel(t[0, j, i]) for i in range(4)])
+        print("  step", j, [rel(t[0, j, i]) for i in range(7)])
 print("softmax warp 4 [S seen, max done, rescale done, exps done, P published]")
 for j in range(8):
     if t[1, j, 0] > 0:
