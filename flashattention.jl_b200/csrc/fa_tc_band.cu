@@ -15,7 +15,9 @@
 //   * each 32-column chunk is classified per warp against the band (inside / outside / mixed): only mixed chunks
 //     pay the per-element select, chunks outside the band of all 32 rows are neither read nor exponentiated.
 // Measured at config 4 (N = 16384, W = 255, B = 512, bf16; same box): two-CTA pair kernel 2.317 ms, this kernel
-// with three CTAs 1.811 ms, with four 1.645 ms (profiles/r1t_band_kernel.md).
+// with three CTAs 1.811 ms, with four 1.645 ms; one-sided masks written back once 1.512 ms; chunk 0 kept in
+// registers between the passes and PV(j) + QK(j+1) handed to the pipe by one elected lane 1.425 ms
+// (profiles/r1t_band_kernel.md).
 // Per step the CTA is serial (QK(j) -> softmax(j) -> PV(j) -> QK(j+1)); the other two CTAs fill the gaps.
 // Layout, descriptors and masking are those of fa_tc_fwd.cu (token-contiguous [B][d][N], SWIZZLE_128B boxes of
 // 64 tokens x 64 channels, MN-major Q/K for S = Q K^T, K-major V for O = P V).
@@ -169,27 +171,30 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       const uint32_t tS = tmem_base + C::COL_S, tO = tmem_base + C::COL_O;
       mbar_wait(bar(C::BAR_QFULL), 0);
       BTRACE(0, 15, 2);                                     // Q landed
-      for (int j = 0; j < nj; ++j) {
-        const int s = j % C::STAGES;
-        const uint32_t par = (uint32_t)(j / C::STAGES) & 1u;
-        // S = Q K(j)^T.  PV(j-1), which read P out of this buffer, was issued before: the tensor pipe runs in order.
-        mbar_wait(bar(C::BAR_KFULL + s), par);
-        BTRACE(0, j, 0);                                    // K(j) ready
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t kd = kdesc + (uint64_t)(s * (C::BOX_BYTES >> 4));
+      // S(0) = Q K(0)^T
+      mbar_wait(bar(C::BAR_KFULL), 0);
+      BTRACE(0, 0, 0);                                      // K(0) ready
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tS, qdesc + (uint64_t)(ks * 128), kd + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
-          BTRACE_E(0, j, 4);                                // QK MMAs handed to the pipe (elected lane)
-          tc_commit(bar(C::BAR_SFULL));          // also: every earlier MMA (PV(j-1)) has completed
-          tc_commit(bar(C::BAR_KEMPTY + s));
-        }
-        __syncwarp();
-        BTRACE(0, j, 1);                                    // QK(j) issued
-        // O += P(j) V(j)
+        for (int ks = 0; ks < D / 16; ++ks)
+          mma_ss(tS, qdesc + (uint64_t)(ks * 128), kdesc + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
+        BTRACE_E(0, 0, 4);
+        tc_commit(bar(C::BAR_SFULL));
+        tc_commit(bar(C::BAR_KEMPTY));
+      }
+      __syncwarp();
+      BTRACE(0, 0, 1);                                      // QK(0) issued
+      for (int j = 0; j < nj; ++j) {
+        const int s = j % C::STAGES, s1 = (j + 1) % C::STAGES;
+        const uint32_t par = (uint32_t)(j / C::STAGES) & 1u, par1 = (uint32_t)((j + 1) / C::STAGES) & 1u;
+        const bool more = j + 1 < nj;
+        // operands of this step's PV and of the next step's QK arrive long before P(j): wait for them first, so
+        // that once P(j) is published one elected lane hands PV(j) AND QK(j+1) to the pipe back to back.
+        // (QK(j+1) overwrites the S buffer PV(j) reads P from: the tensor pipe runs in order.)
         mbar_wait(bar(C::BAR_VFULL + s), par);
-        BTRACE(0, j, 5);                                    // V(j) ready
+        if (more) mbar_wait(bar(C::BAR_KFULL + s1), par1);
+        BTRACE(0, j, 5);                                    // V(j), K(j+1) ready
         chain_wait(bar(C::BAR_PFULL), (uint32_t)j & 1u);
         BTRACE(0, j, 2);                                    // P(j) seen
         tc_fence_after();
@@ -198,11 +203,20 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 #pragma unroll
           for (int ks = 0; ks < BN / 16; ++ks)
             mma_ts(tO, tS + ks * 8, vd + (uint64_t)(ks * 2), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
-          BTRACE_E(0, j, 6);                                // PV MMAs handed to the pipe (elected lane)
+          BTRACE_E(0, j, 6);                                // PV MMAs handed to the pipe
           tc_commit(bar(C::BAR_VEMPTY + s));
+          if (more) {
+            const uint64_t kd = kdesc + (uint64_t)(s1 * (C::BOX_BYTES >> 4));
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks)
+              mma_ss(tS, qdesc + (uint64_t)(ks * 128), kd + (uint64_t)(ks * 128), idesc_qk, ks > 0 ? 1u : 0u);
+            BTRACE_E(0, j + 1, 4);                          // QK(j+1) MMAs handed to the pipe
+            tc_commit(bar(C::BAR_SFULL));        // also: every earlier MMA (PV(j)) has completed
+            tc_commit(bar(C::BAR_KEMPTY + s1));
+          }
         }
         __syncwarp();
-        BTRACE(0, j, 3);                                    // PV(j) issued
+        BTRACE(0, j, 3);                                    // PV(j) (+ QK(j+1)) issued
       }
       if (elect_one()) tc_commit(bar(C::BAR_OFINAL));
       __syncwarp();
@@ -303,9 +317,10 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         uint32_t s0[32], s1[TWO_PASS ? 1 : 32];
         float mx = -INFINITY;
         if (TWO_PASS) {
-          // ---- pass 1: row max, one chunk in registers at a time
+          // ---- pass 1: row max, one chunk in registers at a time; chunk 0 last, so that it is still in registers
+          // when pass 2 starts with it
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 1; c >= 0; --c) {
             if (kc[c] != 2u) {
               tmem_ld32(tS + 32 * c, s0);
               tmem_wait_ld();
@@ -355,8 +370,10 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             if (kc[c] == 2u) { zero16(tS + 16 * c); continue; }
-            tmem_ld32(tS + 32 * c, s0);
-            tmem_wait_ld();
+            if (c == 1) {                          // chunk 0 is still in registers from pass 1
+              tmem_ld32(tS + 32, s0);
+              tmem_wait_ld();
+            }
             exp32(s0, negm2, tS + 16 * c);
           }
         } else {
