@@ -234,6 +234,23 @@ def test_circulant_fwd_tc(N, d, B, W, dtype):
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
 
 
+@pytest.mark.parametrize("N", [64, 128, 192, 320])
+def test_circulant_band_kernel_window_sweep(N):
+    """The compact band kernel (csrc/fa_tc_band.cu: d = 64, four CTAs per SM, per-32-column band classification)
+    over the window sizes that move the band edges through every chunk position: 1 key, chunk and tile boundaries
+    +-1, the whole sequence; a partial last query tile (N = 64, 192, 320); bf16, 2e-3 against the oracle."""
+    for W in (1, 2, 31, 32, 33, 63, 64, 65, 127, N):
+        if W > N:
+            continue
+        Q, K, V = _qkv((N, 64, 3), 64, BF16)
+        O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (Q, K, V)), W)
+        O, l, m = fa.circulant_fa(*(to_dev(t, BF16) for t in (Q, K, V)), W)
+        assert fa.last_path() == "tc"
+        assert rel_err(to_np(O), O0, BF16) < 2e-3, (N, W)
+        assert rel_err(to_np(l), l0) < 2e-3, (N, W)
+        assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max()), (N, W)
+
+
 @pytest.mark.parametrize("N,d,B,W,dtype", [(64, 8, 2, 9, F32), (128, 16, 2, 16, F32), (300, 64, 1, 65, F32),
                                            (256, 64, 2, 33, BF16)])
 def test_circulant_bwd(N, d, B, W, dtype):
