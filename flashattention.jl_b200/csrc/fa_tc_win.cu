@@ -103,7 +103,14 @@ struct WinParams {
   WinMap mp;
   long long ngroups, nwin;
   float scale_log2;
+  long long* trace;  // FA_TRACE builds: CTA 1 records clock64() per phase of its first 16 iterations
 };
+
+#ifdef FA_TRACE
+#define WTRACE(ev) do { if (prm.trace && blockIdx.x == 1 && tid == 0 && it < 16) prm.trace[it * 8 + (ev)] = clock64(); } while (0)
+#else
+#define WTRACE(ev) do {} while (0)
+#endif
 
 // TMAG: the gather is done by TMA instead of per-thread loads (exact-cover windows, stride == W): one 5-D box
 // (x: all windows of the CTA, y: W, z: W, all channels, 1 batch) per tensor lands in a staging buffer --
@@ -300,10 +307,12 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     long long gw0 = grp * mp.nwc;
     int nvalid = mp.nwc, xshift = 0;
     if (TMAG) { int x0, y0, z0, b; decode(grp, gw0, nvalid, x0, y0, z0, b); xshift = (x0 + 1024) & 7; }
+    WTRACE(0);                                           // iteration start
     build_wininfo(g, mp, gw0, prm.nwin, wininfo, tid, nvalid);
     __syncthreads();
     build_table(g, mp, wininfo, D, tsrc, trow, tid, C::THREADS);
     __syncthreads();
+    WTRACE(1);                                           // tables built
 
     if (TMAG) {
       // ---- gather by TMA + shared -> shared repack (8 table entries per lane held in registers per pass)
@@ -364,6 +373,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     }
     fence_proxy_async();
     __syncthreads();
+    WTRACE(2);                                           // gather done
 
     // ---- S = Q K^T per tile (M = 128 rows, N = 128 columns, K = D channels)
     if (warp == 0) {
@@ -384,6 +394,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     const long long gw = gw0 + (long long)ti * mp.G + wi;
     const bool valid = wi < mp.G && gw < prm.nwin && ti * mp.G + wi < nvalid;
     mbar_wait(bar_s, it & 1u);
+    WTRACE(3);                                           // S ready
     tc_fence_after();
 
     // ---- softmax over the columns of this row's window (block-diagonal mask).  Each 32-column chunk
@@ -461,6 +472,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     tmem_wait_st();
     tc_fence_before();
     __syncthreads();
+    WTRACE(4);                                           // softmax done (all warps)
 
     // ---- O = P V per tile (A = P from TMEM, B = V K-major, K = 128 keys)
     if (warp == 0) {
@@ -484,6 +496,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     }
     const float inv_l = valid ? 1.f / lsum : 0.f;      // rows no window maps to: O row is never scattered
     mbar_wait(bar_o, it & 1u);
+    WTRACE(5);                                           // O ready
     tc_fence_after();
 
     // ---- O rows -> fp32 staging [channel][128 rows] over the dead Q and K tiles of this tile
@@ -498,6 +511,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    WTRACE(6);                                           // O staged
 
     // ---- scatter (fused `unwindow` / fold) with the gather's lane mapping
     {
@@ -525,6 +539,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
       }
     }
     __syncthreads();      // staging (= Q/K tiles), table and TMEM are free for the next iteration
+    WTRACE(7);                                           // scatter issued
   }
 
   tc_fence_before();
@@ -946,6 +961,10 @@ int launch_win_fwd(const Geo& g, const FwdArgs& a, cudaStream_t st) {
   prm.nwin = g.L * g.B;
   prm.ngroups = (prm.nwin + prm.mp.nwc - 1) / prm.mp.nwc;
   prm.scale_log2 = g.tau * LOG2E;
+  prm.trace = nullptr;
+#ifdef FA_TRACE
+  { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
