@@ -195,7 +195,7 @@ def main():
     per_gpu = value / world
 
     # ---- the other legs of the named config and of the sharded configs (not part of `value`):
-    #      dense backward at the same shape, circulant C4 and windowed C5 forward/backward per GPU
+    #      dense backward at the same shape, circulant C4, windowed C5 and C2 forward/backward per GPU
     extra = None
     if not args.no_extra:
         def timeit(fn, reps):
@@ -254,6 +254,35 @@ def main():
                                   "fwd_frac_hbm_peak": byf / tf_ / 1e6 / peaks_x["hbm_gbs"], "bwd_frac_hbm_peak": byb / tw_ / 1e6 / peaks_x["hbm_gbs"],
                                   "tokens_per_s_fwd": Bw * ntok * world / tf_ * 1e3, "path": pf + "/" + fa.last_path()}
         del wq, wk, wv, wg, wy, wl, wm
+        torch.cuda.empty_cache()
+        # C2: windowed 2-D forward + backward, 64x64 image, W=7 (stride 7, pad 3), d=64, B=8 (a 17 MB problem: one wave of
+        # CTAs, so the calls are captured into a CUDA graph -- GPU time without the Python wrapper / launch latency)
+        def graph_time(fn, reps):
+            fn(); torch.cuda.synchronize()
+            st_ = torch.cuda.Stream()
+            with torch.cuda.stream(st_):
+                fn()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=st_):
+                    for _ in range(reps):
+                        fn()
+            torch.cuda.synchronize()
+            g_.replay(); torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g_.replay(); b_.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / reps
+        iq, ik, iv, ig = (fa.jl_empty((64, 64, 64, 8), bf, dev).normal_() for _ in range(4))
+        iy, il, im = fa.windowed_fa(iq, ik, iv, 7, 7, 3)
+        t2f = graph_time(lambda: fa.windowed_fa(iq, ik, iv, 7, 7, 3), 20)
+        p2 = fa.last_path()
+        t2b = graph_time(lambda: fa.windowed_fa_backward(iq, ik, iv, ig, il, im, 7, 7, 3), 20)
+        by2f = (4 * 4096 * 64 * 2) * 8 + 8 * 49 * 100 * 8
+        by2b = (7 * 4096 * 64 * 2) * 8 + 8 * 49 * 100 * 8
+        extra["C2_windowed2d"] = {"batch": 8, "fwd_ms": t2f, "bwd_ms": t2b, "timing": "CUDA graph of 20 calls, per call",
+                                  "fwd_alg_gbs": by2f / t2f / 1e6, "bwd_alg_gbs": by2b / t2b / 1e6,
+                                  "fwd_frac_hbm_peak": by2f / t2f / 1e6 / peaks_x["hbm_gbs"], "bwd_frac_hbm_peak": by2b / t2b / 1e6 / peaks_x["hbm_gbs"],
+                                  "path": p2 + "/" + fa.last_path()}
+        del iq, ik, iv, ig, iy, il, im
         torch.cuda.empty_cache()
 
     # ---- end to end: host (pinned) buffers through the public API, H2D + kernel + D2H every step

@@ -81,6 +81,10 @@ struct BandParams {
 
 // FA_BAND_SPIN: poll the two hand-off barriers of the per-step chain (S ready -> softmax, P ready -> issuer) with
 // the non-suspending test_wait instead of try_wait (which may park the thread for a system-dependent time)
+// FA_BAND_EMU: column pairs (of the 4 per block of 8) whose exponentials are evaluated on the FMA pipe instead of MUFU
+#ifndef FA_BAND_EMU
+#define FA_BAND_EMU 0
+#endif
 #ifndef FA_BAND_SPIN
 #define FA_BAND_SPIN 0
 #endif
@@ -280,7 +284,24 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         for (int u = 0; u < 4; ++u)
           x[u] = __ffma2_rn(make_float2(__uint_as_float(sc[e0 + 2 * u]), __uint_as_float(sc[e0 + 2 * u + 1])), scale2, negm2);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { x[u].x = ex2(x[u].x); x[u].y = ex2(x[u].y); }
+        for (int u = 0; u < 4; ++u) {
+          if (u >= 4 - FA_BAND_EMU) {
+            // exponential on the FMA pipe (Cody-Waite split + cubic, rel. error 9e-5 << 16-bit rounding of P)
+            float2 t = x[u];
+            t.x = fmaxf(t.x, -126.f); t.y = fmaxf(t.y, -126.f);
+            const float2 xf = __fadd2_rd(t, make_float2(12582912.f, 12582912.f));
+            const float2 xr = __fadd2_rn(xf, make_float2(-12582912.f, -12582912.f));
+            const float2 fr = __fadd2_rn(t, make_float2(-xr.x, -xr.y));
+            float2 q = __ffma2_rn(fr, make_float2(0.077119089663028717f, 0.077119089663028717f),
+                                  make_float2(0.227564394474029541f, 0.227564394474029541f));
+            q = __ffma2_rn(q, fr, make_float2(0.695146143436431885f, 0.695146143436431885f));
+            q = __ffma2_rn(q, fr, make_float2(1.f, 1.f));
+            x[u].x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(xf.x) << 23));
+            x[u].y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(xf.y) << 23));
+          } else {
+            x[u].x = ex2(x[u].x); x[u].y = ex2(x[u].y);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (u & 1) l2b = __fadd2_rn(l2b, x[u]); else l2a = __fadd2_rn(l2a, x[u]);
