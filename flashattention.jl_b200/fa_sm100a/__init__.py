@@ -300,12 +300,19 @@ def ring_dense_fa(q, k, v, group=None, flags: int = 0):
     """Ring attention forward for one long sequence sharded by TOKENS over the ranks of ``group``:
     every rank passes its ``(Nl, d, B)`` shard of q, k, v and gets its ``(Nl, dv, B)`` slice of
     ``dense_fa`` over the full sequence, plus ``l, m``.  K/V blocks travel round the ring over NCCL
-    (``fa_ring_dense_fwd``).  Without an initialised process group it degenerates to ``dense_fa``."""
+    (``fa_ring_dense_fwd``).  Without an initialised process group it degenerates to ``dense_fa``.
+    Like ``dense_fa`` (src/dense.jl:1-19) it also takes ``(spatial.., d, B)`` shards -- e.g. one 3-D volume cut along
+    its slowest spatial dim, whose planes are contiguous token ranges -- and returns ``y`` in the shard's shape."""
     import torch.distributed as dist
     _same(q, k, v)
     q, k, v = (jl_array(t) for t in (q, k, v))
-    if q.ndim != 3 or not q.is_cuda:
-        raise FaError("ring_dense_fa: q, k, v must be CUDA tensors of shape (N_local, d, B)")
+    if q.ndim < 3 or not q.is_cuda:
+        raise FaError("ring_dense_fa: q, k, v must be CUDA tensors of shape (N_local, d, B) or (spatial.., d, B)")
+    if q.ndim > 3:
+        spatial = tuple(int(s) for s in q.shape[:-2])
+        q3, k3, v3 = (_jl_reshape(t, (-1,) + tuple(t.shape[-2:])) for t in (q, k, v))
+        O, l, m = ring_dense_fa(q3, k3, v3, group=group, flags=flags)
+        return _jl_reshape(O, spatial + tuple(O.shape[-2:])), l, m
     Nl, d, B = (int(s) for s in q.shape)
     dv = int(v.shape[1])
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -333,6 +340,11 @@ def ring_dense_fa_backward(q, k, v, O, dO, l, m, group=None, flags: int = 0):
     _same(q, k, v, O, dO)
     q, k, v, O, dO = (jl_array(t) for t in (q, k, v, O, dO))
     l, m = (jl_array(t, torch.float32) for t in (l, m))
+    if q.ndim > 3:                                           # (spatial.., d, B) shards: flatten like dense_fa
+        shapes = [tuple(t.shape) for t in (q, k, v)]
+        flat = lambda t: _jl_reshape(t, (-1,) + tuple(t.shape[-2:]))
+        grads = ring_dense_fa_backward(flat(q), flat(k), flat(v), flat(O), flat(dO), l, m, group=group, flags=flags)
+        return tuple(_jl_reshape(g_, sh) for g_, sh in zip(grads, shapes))
     Nl, d, B = (int(s) for s in q.shape)
     dv = int(v.shape[1])
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1

@@ -38,6 +38,15 @@ function ring_dense_fa(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T, 3}, com
     return O, l, m
 end
 
+"`ring_dense_fa` on `(spatial..., d, B)` shards (e.g. a 3-D volume cut along its slowest spatial dim): flattened like `dense_fa` (src/dense.jl:1-19)."
+function ring_dense_fa(q::CuArray{T, N}, k::CuArray{T, N}, v::CuArray{T, N}, comm::Ptr{Cvoid},
+                       rank::Integer, nranks::Integer; flags::Integer=0) where {T, N}
+    sz = size(q)[1:N-2]
+    r3(x) = reshape(x, :, size(x, N-1), size(x, N))
+    O, l, m = ring_dense_fa(r3(q), r3(k), r3(v), comm, rank, nranks; flags=flags)
+    return reshape(O, sz..., size(O, 2), size(O, 3)), l, m
+end
+
 "Backward of `ring_dense_fa`: pass the shards and the `(O, l, m)` the ring forward returned."
 function ring_dense_fa_backward(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T, 3}, O::CuArray{T, 3}, dO::CuArray{T, 3},
                                 l::CuArray{Float32, 3}, m::CuArray{Float32, 3}, comm::Ptr{Cvoid},

@@ -201,6 +201,23 @@ def test_ring_backward_single_rank_equals_dense(dtype, N, d):
 
 
 @pytest.mark.gpu
+def test_ring_accepts_volume_shards():
+    """A 3-D volume shard ``(X, Y, Z_local, d, B)`` (planes of the slowest spatial dim = contiguous tokens) goes through
+    the ring entry points like ``dense_fa`` takes N-D inputs (src/dense.jl:1-19); one rank: equals ``dense_fa``."""
+    import fa_sm100a as fa
+    dtype = torch.bfloat16
+    q, k, v, g = (to_dev(randn_np((8, 8, 8, 128, 2), s, dtype), dtype) for s in range(4))
+    y0, l0, m0 = fa.dense_fa(q, k, v)
+    y, l, m = fa.ring_dense_fa(q, k, v)
+    assert tuple(y.shape) == (8, 8, 8, 128, 2) and rel_err(to_np(y), to_np(y0).astype(np.float64), dtype, want_rounded=True) < 2e-3
+    grads = fa.ring_dense_fa_backward(q, k, v, y, g, l, m)
+    want = fa.dense_fa_backward(*(fa._jl_reshape(t, (-1, 128, 2)) for t in (q, k, v, y, g)), l, m)
+    for a, b in zip(grads, want):
+        assert tuple(a.shape) == (8, 8, 8, 128, 2)
+        assert rel_err(to_np(a).reshape((512, 128, 2), order="F"), to_np(b).astype(np.float64), dtype, want_rounded=True) < 2e-3
+
+
+@pytest.mark.gpu
 def test_merge_partials_kernel():
     import ctypes
     import fa_sm100a as fa
