@@ -56,7 +56,7 @@ def main():
             if re.search(pat, line):
                 counts[cur][key] += 1
     dm = demangle(list(counts))
-    want = sys.argv[1] if len(sys.argv) > 1 else r"tc_|ring|merge|circ2d|softmax"
+    want = sys.argv[1] if len(sys.argv) > 1 else r"tc_|band|ring|merge|circ2d|softmax"
     keys = [k for k, _ in PATTERNS]
     print("# SASS census of lib/libfa_sm100a.so (cuobjdump -sass / -res-usage, sm_100a)\n")
     print("`UTC*MMA` = tcgen05.mma, `LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = cp.async.bulk.tensor, `SYNCS` = mbarrier ops,")
