@@ -204,14 +204,19 @@ int fa_circulant2d_index(int64_t X, int64_t Y, int64_t W, int64_t* keys) {
 
 int fa_circulant2d_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
                        int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags, void* stream) {
-  (void)flags;
   C2Params g;
   int rc = check(X, Y, d, dv, B, W, dtype, g);
   if (rc) return rc;
   if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
   if ((rc = device_ok())) return rc;
-  set_path("simt");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // 16-bit, d = dv = 64, X % 64 == 0: the tcgen05 band kernel walking W key rows (fa_tc_band.cu)
+  const bool aligned = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (!(flags & FA_FLAG_FORCE_SIMT) && aligned && tc_band2d_supported(X, Y, d, dv, B, W, dtype)) {
+    set_path("tc");
+    return tc_band2d_fwd(q, k, v, o, l, m, X, Y, B, W, dtype, st);
+  }
+  set_path("simt");
   if (dtype == FA_F32) return fwd_t<float>(q, k, v, o, l, m, g, st);
   if (dtype == FA_F16) return fwd_t<__half>(q, k, v, o, l, m, g, st);
   return fwd_t<__nv_bfloat16>(q, k, v, o, l, m, g, st);

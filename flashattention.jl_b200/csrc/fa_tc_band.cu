@@ -23,6 +23,8 @@
 // 64 tokens x 64 channels, MN-major Q/K for S = Q K^T, K-major V for O = P V).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+#include <math.h>
 #include "fa_common.cuh"
 #include "fa_ptx.cuh"
 
@@ -58,6 +60,7 @@ struct BandParams {
   void* o;
   float *l, *m;
   int N, W, p;
+  int X, Y;              // TD (2-D periodic neighbourhood): image extents, N = X * Y, tokens x-fastest
   float scale_log2;
   long long* trace;      // FA_TRACE builds: one CTA in the middle of the grid records clock64() per event
 };
@@ -109,7 +112,7 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int FMT, int CTAS>
+template <int FMT, int CTAS, int TD>
 __global__ void __launch_bounds__(BandCfg<CTAS>::THREADS, BandCfg<CTAS>::CTAS_PER_SM)
 tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                const __grid_constant__ CUtensorMap tmv, const BandParams prm) {
@@ -121,7 +124,14 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   auto bar = [&](int i) { return sbase + C::OFF_BAR + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = sbase + C::OFF_TMEM_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, b = blockIdx.y;
+  // 1-D: query tile = 128 consecutive tokens.  TD: query tile = up to 128 consecutive x of ONE image row yq
+  // (tokens are x-fastest, X % 64 == 0), blockIdx.x = row * tiles_per_row + tile.
+  const int b = blockIdx.y;
+  const int tpr = TD ? (prm.X + 127) / 128 : 1;
+  const int yq = TD ? (int)(blockIdx.x / tpr) : 0;
+  const int x0 = TD ? (int)(blockIdx.x % tpr) * 128 : 0;
+  const int tq = TD ? (prm.X - x0 < 128 ? prm.X - x0 : 128) : 128;
+  const int q0 = TD ? yq * prm.X + x0 : blockIdx.x * 128;
   if (warp == 1) BTRACE(0, 15, 0);                         // kernel entry
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv); }
@@ -144,8 +154,23 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 
   // key tiles of this query tile: keys (q - p) .. (q - p + W - 1) for q in [q0, q0 + 128), from the 64-aligned
   // tile at or below q0 - p (src/circulant.jl:61-67: the window of query j starts p keys before it, periodic)
-  const int kbase = fdiv(q0 - prm.p, BN) * BN;
-  const int nj = fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1;
+  // TD: the keys of (x, y) are (mod(x - p + s, X), mod(y - p + t, Y)), s, t in [0, W) -- the direct product of the
+  // 1-D key set (src/utils.jl:6-17).  Steps = W key rows x the nx 64-key tiles of a row that meet the x band of the
+  // query tile (all X / 64 tiles of the row, once each, when the band wraps round the whole row).
+  const int kbase = TD ? fdiv(x0 - prm.p, BN) * BN : fdiv(q0 - prm.p, BN) * BN;
+  int nx = 1, kxb = kbase;
+  if (TD) {
+    nx = fdiv(x0 + tq - 1 - prm.p + prm.W - 1 - kbase, BN) + 1;
+    if (nx * BN >= prm.X) { nx = prm.X / BN; kxb = 0; }
+  }
+  const int nj = TD ? prm.W * nx : fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1;
+  // token of the first key of step j (TD: row (yq - p + t) mod Y, x tile (kxb + 64 jx) mod X)
+  auto key_tile = [&](int j, int& kxs) {
+    if (!TD) { kxs = 0; return (int)pmod(kbase + BN * j, prm.N); }
+    const int t = j / nx, jx = j - t * nx;
+    kxs = (int)pmod(kxb + BN * jx, prm.X);
+    return (int)pmod(yq - prm.p + t, prm.Y) * prm.X + kxs;
+  };
 
   if (warp < 4) {
     if (CTAS == 4) setmaxnreg_dec<32>(); else setmaxnreg_dec<40>();
@@ -157,7 +182,8 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       for (int j = 0; j < nj; ++j) {
         const int s = j % C::STAGES;
         const uint32_t par = ((uint32_t)(j / C::STAGES) & 1u) ^ 1u;
-        const int tok = (int)pmod(kbase + BN * j, prm.N);
+        int kxs_unused;
+        const int tok = key_tile(j, kxs_unused);
         mbar_wait(bar(C::BAR_KEMPTY + s), par);
         mbar_arrive_expect_tx(bar(C::BAR_KFULL + s), C::BOX_BYTES);
         tma_load_3d(sK + s * C::BOX_BYTES, &tmk, bar(C::BAR_KFULL + s), tok, 0, b);
@@ -236,7 +262,8 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     const float2 scale2 = make_float2(scale, scale);
     float m_true = -INFINITY, m_used = -INFINITY;
     float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
-    const int lo0 = (qi - prm.p) - kbase;                       // first in-band column of key tile 0 for this row
+    const int lo0 = (qi - prm.p) - kbase;                       // 1-D: first in-band column of key tile 0 for this row
+    const int qx = x0 + row;                                    // TD: image column of this row's query
 
     // x16 TMEM load (rescale of O in 16-column pieces keeps the register peak low)
     auto tmem_ld16 = [](uint32_t taddr, uint32_t (&o)[16]) {
@@ -264,6 +291,12 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         for (int e = 0; e < 32; ++e)
           if (e < lo || e >= hi) sc[e] = 0xff800000u;
       }
+    };
+    // TD, band wrapping round the image row inside one key tile: a second interval [lo2, hi2)
+    auto mask32_2 = [](uint32_t (&sc)[32], int lo, int hi, int lo2, int hi2) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (!((e >= lo && e < hi) || (e >= lo2 && e < hi2))) sc[e] = 0xff800000u;
     };
     auto max32 = [](const uint32_t (&sc)[32]) {
       float a = -INFINITY, bq = -INFINITY;
@@ -319,14 +352,30 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 
 #pragma unroll 1
     for (int j = 0; j < nj; ++j) {
-      const int lo = lo0 - BN * j, hi = lo + prm.W;            // lo <= col < hi stays
+      // valid columns of this key tile for this row: [lo, hi), and for TD also [lo2, hi2) = the same band one image
+      // row length to the left (periodic in x): (c - a) mod X < W with a = (qx - p - tile start) mod X
+      int lo, hi, lo2 = 0, hi2 = 0;
+      if (TD) {
+        int kxs;
+        key_tile(j, kxs);
+        lo = (int)pmod(qx - prm.p - kxs, prm.X); hi = lo + prm.W;
+        lo2 = lo - prm.X; hi2 = lo2 + prm.W;
+      } else {
+        lo = lo0 - BN * j; hi = lo + prm.W;
+      }
+      const bool two = TD && __any_sync(0xffffffffu, hi2 > 0);       // warp-uniform: some lane's band wraps into this tile
       // Each 32-column chunk is classified per warp (the band edge is a diagonal: it crosses ~32 columns over a
       // warp's 32 rows): 1 = inside the band of every lane (no predicates), 2 = outside for every lane (P = 0: S is
       // not read, no exponentials), 0 = mixed (per-element select).
       uint32_t kc[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const bool in = lo <= 32 * c && 32 * c + 32 <= hi, out = hi <= 32 * c || lo >= 32 * c + 32;
+        bool in = lo <= 32 * c && 32 * c + 32 <= hi, out = hi <= 32 * c || lo >= 32 * c + 32;
+        if (TD) {
+          const int c1 = min(hi, 32 * c + 32) - max(lo, 32 * c), c2 = min(hi2, 32 * c + 32) - max(lo2, 32 * c);
+          const int cnt = (c1 > 0 ? c1 : 0) + (c2 > 0 ? c2 : 0);
+          in = cnt == 32; out = cnt == 0;
+        }
         kc[c] = __all_sync(0xffffffffu, in) ? 1u : (__all_sync(0xffffffffu, out) ? 2u : 0u);
       }
       chain_wait(bar(C::BAR_SFULL), (uint32_t)j & 1u);
@@ -346,7 +395,8 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
               tmem_ld32(tS + 32 * c, s0);
               tmem_wait_ld();
               if (kc[c] == 0u) {                    // masked once: pass 2 reads the masked chunk back
-                mask32(s0, lo - 32 * c, hi - 32 * c);
+                if (two) mask32_2(s0, lo - 32 * c, hi - 32 * c, lo2 - 32 * c, hi2 - 32 * c);
+                else mask32(s0, lo - 32 * c, hi - 32 * c);
                 tmem_st32(tS + 32 * c, s0);
               }
               mx = fmaxf(mx, max32(s0));
@@ -357,8 +407,11 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           if (kc[0] != 2u) tmem_ld32(tS, s0);
           if (kc[1] != 2u) tmem_ld32(tS + 32, (uint32_t(&)[32])s1);
           tmem_wait_ld();
-          if (kc[0] == 0u) mask32(s0, lo, hi);
-          if (kc[1] == 0u) mask32((uint32_t(&)[32])s1, lo - 32, hi - 32);
+          if (kc[0] == 0u) { if (two) mask32_2(s0, lo, hi, lo2, hi2); else mask32(s0, lo, hi); }
+          if (kc[1] == 0u) {
+            if (two) mask32_2((uint32_t(&)[32])s1, lo - 32, hi - 32, lo2 - 32, hi2 - 32);
+            else mask32((uint32_t(&)[32])s1, lo - 32, hi - 32);
+          }
           if (kc[0] != 2u) mx = max32(s0);
           if (kc[1] != 2u) mx = fmaxf(mx, max32((uint32_t(&)[32])s1));
         }
@@ -415,7 +468,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     if (warp == 4) BTRACE(1, 15, 0);                        // all MMAs done
     tc_fence_after();
     const float inv_l = 1.f / l_run;
-    const bool in_range = qi < prm.N;
+    const bool in_range = TD ? row < tq : qi < prm.N;
     unsigned short* ob = static_cast<unsigned short*>(prm.o) + (size_t)b * D * prm.N + qi;
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
@@ -444,8 +497,8 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int FMT, int CTAS>
-int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
+template <int FMT, int CTAS, int TD>
+int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int X = 0, int Y = 0) {
   using C = BandCfg<CTAS>;
   CUtensorMap tmq, tmk, tmv;
   int rc;
@@ -455,14 +508,15 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   BandParams prm;
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.W = g.W; prm.p = g.p;
+  prm.X = X; prm.Y = Y;
   prm.scale_log2 = g.tau * LOG2E;
   prm.trace = nullptr;
 #ifdef FA_TRACE
   { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
 #endif
-  auto kern = tc_band_kernel<FMT, CTAS>;
+  auto kern = tc_band_kernel<FMT, CTAS, TD>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.B);
+  const dim3 grid(TD ? (unsigned)(((X + 127) / 128) * Y) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
@@ -473,8 +527,29 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
 // circulant, d = dv = 64, 16-bit output, tile-aligned wrap-around (N % 64 == 0) -- checked by the caller (tc_fwd)
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
-  if (ctas != 3) return dtype == FA_BF16 ? launch_band<1, 4>(g, a, dtype, st) : launch_band<0, 4>(g, a, dtype, st);
-  return dtype == FA_BF16 ? launch_band<1, 3>(g, a, dtype, st) : launch_band<0, 3>(g, a, dtype, st);
+  if (ctas != 3) return dtype == FA_BF16 ? launch_band<1, 4, 0>(g, a, dtype, st) : launch_band<0, 4, 0>(g, a, dtype, st);
+  return dtype == FA_BF16 ? launch_band<1, 3, 0>(g, a, dtype, st) : launch_band<0, 3, 0>(g, a, dtype, st);
+}
+
+// 2-D periodic neighbourhood attention on (X, Y, 64, B), 16-bit: the same kernel walking W key rows
+bool tc_band2d_supported(long long X, long long Y, long long d, long long dv, long long B, long long W, int dtype) {
+  if (dtype != FA_BF16 && dtype != FA_F16) return false;
+  if (d != 64 || dv != 64 || X % 64 != 0 || X <= 0 || Y <= 0 || W <= 0 || W > X || W > Y || W > 64) return false;
+  if (B > 65535 || X * Y > 0x3fffffffLL || ((X + 127) / 128) * Y > 0x7fffffffLL) return false;
+  return true;
+}
+
+int tc_band2d_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                  long long X, long long Y, long long B, long long W, int dtype, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) {
+    set_error("tc_band2d_fwd: q/k/v must be 16-byte aligned"); return FA_ERR_INVALID;
+  }
+  Geo g;
+  memset(&g, 0, sizeof(g));
+  g.mode = MODE_CIRCULANT; g.d = 64; g.dv = 64; g.N = X * Y; g.B = B; g.W = (int)W; g.p = (int)((W - 1) / 2);
+  g.tau = 1.0f / sqrtf(64.f);
+  FwdArgs a{q, k, v, o, nullptr, l, m};
+  return dtype == FA_BF16 ? launch_band<1, 4, 1>(g, a, dtype, st, (int)X, (int)Y) : launch_band<0, 4, 1>(g, a, dtype, st, (int)X, (int)Y);
 }
 
 }  // namespace fa

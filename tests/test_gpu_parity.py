@@ -532,6 +532,30 @@ def test_circulant2d_fwd_bwd(X, Y, d, B, W, dtype):
         assert rel_err(to_np(a), b_, dtype) < btol
 
 
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("X,Y,B,W", [(64, 9, 2, 7), (128, 5, 1, 5), (192, 16, 2, 16), (64, 64, 1, 3), (256, 7, 1, 1),
+                                     (128, 16, 2, 13), (320, 4, 1, 4), (64, 3, 1, 2)])
+def test_circulant2d_fwd_tc(X, Y, B, W, dtype):
+    """2-D periodic neighbourhood attention on the tcgen05 band kernel (16-bit, d = 64, X % 64 == 0): the kernel
+    walks W key rows x the 64-key tiles of a row, band edges and the wrap round the image row masked in registers.
+    2e-3 against the oracle (direct product of the 1-D key set); X = 64 exercises the band wrapping inside one tile,
+    X = 128 the all-tiles-of-the-row case, X >= 192 distinct tiles.  The backward (exact fp32 kernels) then takes
+    the (O, l, m) the tcgen05 forward produced."""
+    d = 64
+    q, k, v, g = (randn_np((X, Y, d, B), s, dtype) for s in range(4))
+    O0, l0, m0 = fo.circulant2d_fa(*(t.astype(np.float64) for t in (q, k, v)), W)
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    O, l, m = fa.circulant_fa(Q, K, V, W)
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(O), O0, dtype) < 2e-3
+    assert rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
+    want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
+    got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < 4e-3      # D = rowsum(dO o O) from the 16-bit O, P from the 16-bit-compute (l, m)
+
+
 def test_circulant2d_rejects_bad_window():
     q = fa.jl_randn((6, 8, 4, 1), 0)
     with pytest.raises(fa.FaError):
