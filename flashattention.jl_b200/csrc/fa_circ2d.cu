@@ -227,19 +227,52 @@ size_t fa_workspace_bytes_circulant2d_bwd(int64_t X, int64_t Y, int64_t B) {
   return ((size_t)X * Y * B * sizeof(float) + 255) & ~(size_t)255;
 }
 
+// geometry of the tcgen05 backward for the 2-D neighbourhood: a circulant Geo that carries the image extents
+static bool tc2d_bwd_geo(Geo& g, int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype) {
+  if (dtype != FA_BF16 && dtype != FA_F16) return false;
+  if (d != dv || (d != 64 && d != 128) || X % 64 != 0 || W > 64) return false;
+  if (((X + 127) / 128) * Y > 0x7fffffffLL) return false;
+  memset(&g, 0, sizeof(g));
+  g.mode = MODE_CIRCULANT; g.d = (int)d; g.dv = (int)dv; g.N = X * Y; g.B = B; g.W = (int)W; g.p = (int)((W - 1) / 2);
+  g.nd = 2; g.s[0] = (int)X; g.s[1] = (int)Y; g.s[2] = 1;
+  g.tau = 1.0f / sqrtf((float)d);
+  return tc_bwd_supported(g, dtype);
+}
+
+// workspace that also admits the tcgen05 backward (16-bit, d = dv in {64, 128}, X % 64 == 0); with only the
+// fa_workspace_bytes_circulant2d_bwd(X, Y, B) amount the exact fp32 kernels run
+size_t fa_workspace_bytes_circulant2d_bwd_ex(int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags) {
+  const size_t base = fa_workspace_bytes_circulant2d_bwd(X, Y, B);
+  Geo g;
+  if (base == 0 || (flags & FA_FLAG_FORCE_SIMT) || !tc2d_bwd_geo(g, X, Y, d, dv, B, W, dtype)) return base;
+  const size_t tc = tc_bwd_workspace_bytes(g, dtype, flags);
+  return tc > base ? tc : base;
+}
+
 int fa_circulant2d_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                        const float* l, const float* m, void* dq, void* dk, void* dv_out,
                        int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  (void)flags;
   C2Params g;
   int rc = check(X, Y, d, dv, B, W, dtype, g);
   if (rc) return rc;
   if (!q || !k || !v || !o || !d_o || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
   if (!workspace || workspace_bytes < fa_workspace_bytes_circulant2d_bwd(X, Y, B)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
   if ((rc = device_ok())) return rc;
-  set_path("simt");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // tcgen05 path: the 1-D circulant backward kernels of fa_tc_bwd.cu walking W image rows (needs the _ex workspace)
+    Geo tg;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                           reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(d_o)) & 15) == 0;
+    if (!(flags & FA_FLAG_FORCE_SIMT) && aligned && tc2d_bwd_geo(tg, X, Y, d, dv, B, W, dtype) &&
+        workspace_bytes >= tc_bwd_workspace_bytes(tg, dtype, flags)) {
+      BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
+      set_path("tc");
+      return tc_bwd(tg, a, dtype, flags, workspace, st);
+    }
+  }
+  set_path("simt");
   float* delta = static_cast<float*>(workspace);
   if (dtype == FA_F32) return bwd_t<float>(q, k, v, o, d_o, l, m, dq, dk, dv_out, delta, g, st);
   if (dtype == FA_F16) return bwd_t<__half>(q, k, v, o, d_o, l, m, dq, dk, dv_out, delta, g, st);

@@ -90,6 +90,7 @@ struct BwdParams {
   int out_f32;           // gradients stored as float32 whatever the input dtype (partials of the ring pass)
   const void *x1, *x2;   // KIND 1: owner tensors (Q, dO) as raw [B][D][N] pointers (loaded straight into TMEM)
   int N, Npad, W, p, mode;
+  int X, Y;              // 2-D periodic neighbourhood (mode circulant, X > 0): image extents, N = X * Y, x fastest
   float scale_log2;      // tau * log2(e)
   float tau;
 };
@@ -206,8 +207,15 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
   const uint32_t tmem_slot = sbase + C::OFF_TMEM_SLOT;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t0 = blockIdx.x * 128, b = blockIdx.y;
+  const int b = blockIdx.y;
   const bool circ = prm.mode == MODE_CIRCULANT;
+  // 2-D (td): the owner tile is up to 128 consecutive x of ONE image row yo; blockIdx.x = row * tiles_per_row + tile
+  const bool td = circ && prm.X > 0;
+  const int tpr = td ? (prm.X + 127) / 128 : 1;
+  const int yo = td ? (int)(blockIdx.x / tpr) : 0;
+  const int x0 = td ? (int)(blockIdx.x % tpr) * 128 : 0;
+  const int tq = td ? (prm.X - x0 < 128 ? prm.X - x0 : 128) : 128;
+  const int t0 = td ? yo * prm.X + x0 : blockIdx.x * 128;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmX1); prefetch_tensormap(&tmX2); prefetch_tensormap(&tmY1); prefetch_tensormap(&tmY2);
@@ -231,7 +239,15 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
 
   // streamed-tile range (unwrapped token coordinates; circulant wraps tile-aligned, N % 64 == 0)
   int cbase = 0, ns = (prm.N + BT - 1) / BT;
-  if (circ) {
+  int nx = 1;
+  if (td) {
+    // streamed tiles = W image rows x the nx 64-token tiles of a row that meet the x band of the owner tile
+    // (keys of (x, y): (mod(x - p + s, X), mod(y - p + t, Y)); queries of a key: the mirror image)
+    if (KIND == 0) { cbase = fdiv(x0 + prm.p - prm.W + 1, BT) * BT; nx = fdiv(x0 + tq - 1 + prm.p - cbase, BT) + 1; }
+    else { cbase = fdiv(x0 - prm.p, BT) * BT; nx = fdiv(x0 + tq - 1 - prm.p + prm.W - 1 - cbase, BT) + 1; }
+    if (nx * BT >= prm.X) { nx = prm.X / BT; cbase = 0; }
+    ns = prm.W * nx;
+  } else if (circ) {
     if (KIND == 0) {   // rows = keys j, cols = queries i with j - (W-1-p) <= i <= j + p
       cbase = fdiv(t0 + prm.p - prm.W + 1, BT) * BT;
       ns = fdiv(t0 + 127 + prm.p - cbase, BT) + 1;
@@ -240,6 +256,15 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       ns = fdiv(t0 + 127 - prm.p + prm.W - 1 - cbase, BT) + 1;
     }
   }
+
+  // first token of streamed tile g; xs = its image column (td)
+  auto stream_tile = [&](int g, int& xs) {
+    if (!td) { xs = 0; return circ ? (int)pmod(cbase + BT * g, prm.N) : BT * g; }
+    const int t = g / nx, jx = g - t * nx;
+    xs = (int)pmod(cbase + BT * jx, prm.X);
+    const int yy = (KIND == 0) ? (int)pmod(yo + prm.p - prm.W + 1 + t, prm.Y) : (int)pmod(yo - prm.p + t, prm.Y);
+    return yy * prm.X + xs;
+  };
 
   if (warp < 4) {
     setmaxnreg_dec<64>();
@@ -254,7 +279,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       }
       for (int g = 0; g < ns; ++g) {
         const int s = g % C::NS;
-        const int tok = circ ? (int)pmod(cbase + BT * g, prm.N) : BT * g;
+        int xs_unused;
+        const int tok = stream_tile(g, xs_unused);
         mbar_wait(bar(C::BAR_EMPTY + s), ((uint32_t)(g / C::NS) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar(C::BAR_FULL + s), C::STAGE_BYTES + (KIND == 0 ? C::STAT_BYTES : 0));
         tma_load_3d(sY + s * C::STAGE_BYTES, &tmY1, bar(C::BAR_FULL + s), tok, 0, b);
@@ -344,7 +370,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
     const float2 scale2 = make_float2(sl2, sl2);
     float2 rnl = make_float2(0.f, 0.f), rnd = make_float2(0.f, 0.f);
     if (KIND == 1) {
-      const float a = prm.nlse[(size_t)b * prm.Npad + row_tok], d = prm.ndelta[(size_t)b * prm.Npad + row_tok];
+      const bool own = !td || row < tq;                    // td: rows past the image row belong to another tile
+      const float a = own ? prm.nlse[(size_t)b * prm.Npad + row_tok] : -INFINITY, d = own ? prm.ndelta[(size_t)b * prm.Npad + row_tok] : 0.f;
       rnl = make_float2(a, a); rnd = make_float2(d, d);
     }
     const int WW = prm.W, pp = prm.p;
@@ -380,8 +407,14 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       const uint32_t stat = sStat + s * C::STAT_BYTES;
       if (KIND == 0) mbar_wait(bar(C::BAR_FULL + s), (uint32_t)(j / C::NS) & 1u);   // nlse / ndelta landed
       // band limits of this step in column units: lo <= col < hi is inside the window
-      int lo = 0, hi = BT;
-      if (circ) {
+      int lo = 0, hi = BT, lo2 = 0, hi2 = 0;                 // td: second interval = the band wrapped round the image row
+      if (td) {
+        int xs;
+        stream_tile(j, xs);
+        const int rx = x0 + row;
+        if (KIND == 0) { hi = (int)pmod(rx + pp - xs, prm.X) + 1; lo = hi - WW; lo2 = lo + prm.X; hi2 = hi + prm.X; }   // (row + p - col) mod X < W
+        else { lo = (int)pmod(rx - pp - xs, prm.X); hi = lo + WW; lo2 = lo - prm.X; hi2 = hi - prm.X; }               // (col - row + p) mod X < W
+      } else if (circ) {
         const int c0 = cbase + BT * j;                       // unwrapped token of column 0
         if (KIND == 0) { hi = row_tok + pp - c0 + 1; lo = hi - WW; }      // 0 <= row + p - col < W
         else { lo = row_tok - pp - c0; hi = lo + WW; }                     // 0 <= col - row + p < W
@@ -403,7 +436,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int col = 32 * c + e;
-            if (col < lo || col >= hi) sc[e] = 0xff800000u;   // -inf -> P = 0, dS = 0
+            if ((col < lo || col >= hi) && (col < lo2 || col >= hi2)) sc[e] = 0xff800000u;   // -inf -> P = 0, dS = 0
           }
         }
 #pragma unroll
@@ -442,7 +475,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
     mbar_wait(bar(C::BAR_ACC), 0);
     tc_fence_after();
     using OT = typename OutT<OBF>::type;
-    const bool in_range = row_tok < prm.N;
+    const bool in_range = td ? row < tq : row_tok < prm.N;
     // KIND 0: warpgroup 0 stores dV (acc0), warpgroup 1 stores tau * dK (acc1);
     // KIND 1: each warpgroup stores half the channels of tau * dQ (acc0)
     const uint32_t tacc = tmem_base + lane_addr + C::COL_ACC + ((KIND == 0 && wg == 1) ? D : 0);
@@ -495,8 +528,11 @@ int launch_tc_bwd(const Geo& g, const BwdArgs& a, const void* q, const void* k, 
   prm.nlse = nlse; prm.ndelta = ndelta; prm.amax = amax;
   prm.x1 = q; prm.x2 = d_o; prm.out_f32 = out_f32;
   prm.N = (int)g.N; prm.Npad = Npad; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
+  // 2-D periodic neighbourhood: a circulant geometry that carries the image extents (nd = 2, s[0] = X, s[1] = Y)
+  const bool td = g.mode == MODE_CIRCULANT && g.nd == 2;
+  prm.X = td ? g.s[0] : 0; prm.Y = td ? g.s[1] : 0;
   prm.scale_log2 = g.tau * LOG2E; prm.tau = g.tau;
-  const dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.B);
+  const dim3 grid(td ? (unsigned)(((g.s[0] + 127) / 128) * g.s[1]) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
   {
     auto kern = tc_bwd_kernel<D, FMT, 0, OBF, 0>;
     FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BCfg<D, 0>::SMEM_BYTES));

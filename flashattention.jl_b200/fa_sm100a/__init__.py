@@ -74,6 +74,7 @@ def _load():
         "fa_circulant2d_index": (ci, [i64, i64, i64, pi64]),
         "fa_circulant2d_fwd": (ci, [vp] * 6 + [i64, i64, i64, i64, i64, i64, ci, ci, vp]),
         "fa_workspace_bytes_circulant2d_bwd": (sz, [i64, i64, i64]),
+        "fa_workspace_bytes_circulant2d_bwd_ex": (sz, [i64, i64, i64, i64, i64, i64, ci, ci]),
         "fa_circulant2d_bwd": (ci, [vp] * 10 + [i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
         "fa_workspace_bytes_windowed_fwd": (sz, [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci]),
         "fa_windowed_fwd": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = (
     "fa_circulant_fwd_host fa_windowed_fwd_host fa_release_host_staging fa_shard_batch fa_merge_partials "
     "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd "
     "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd "
-    "fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd").split()
+    "fa_workspace_bytes_circulant2d_bwd_ex fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd").split()
 
 
 def _check(rc: int, what: str):
@@ -615,7 +616,7 @@ def circulant_fa_backward(Q, K, V, O, dO, l, m, W: int, flags: int = 0):
     if Q.ndim == 4:
         X, Y, d, B = (int(s) for s in Q.shape)
         dQ, dK, dV = (jl_empty(t.shape, t.dtype, t.device) for t in (Q, K, V))
-        ws = _workspace(lib.fa_workspace_bytes_circulant2d_bwd(X, Y, B), Q.device)
+        ws = _workspace(lib.fa_workspace_bytes_circulant2d_bwd_ex(X, Y, d, int(V.shape[2]), B, int(W), _dt(Q), flags), Q.device)
         with torch.cuda.device(Q.device):
             _check(lib.fa_circulant2d_bwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m), _ptr(dQ), _ptr(dK), _ptr(dV),
                                           X, Y, d, int(V.shape[2]), B, int(W), _dt(Q), flags, _ptr(ws), ws.numel(), _stream(Q)),

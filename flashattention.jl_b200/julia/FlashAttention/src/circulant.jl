@@ -73,7 +73,8 @@ function circulant_fa_backward(Q::CuArray{T, 4}, K::CuArray{T, 4}, V::CuArray{T,
     X, Y, d, batchsize = size(Q)
     dv = size(V, 3)
     dQ, dK, dV = similar(Q), similar(K), similar(V)
-    nws = ccall(sym(:fa_workspace_bytes_circulant2d_bwd), Csize_t, (Int64, Int64, Int64), X, Y, batchsize)
+    nws = ccall(sym(:fa_workspace_bytes_circulant2d_bwd_ex), Csize_t, (Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint),
+                X, Y, d, dv, batchsize, W, fa_dtype(T), Cint(flags))
     ws = CuArray{UInt8}(undef, max(nws, 256))
     rc = ccall(sym(:fa_circulant2d_bwd), Cint,
                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},

@@ -108,6 +108,9 @@ int fa_circulant2d_fwd(const void* q, const void* k, const void* v, void* o, flo
                        int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W,
                        int dtype, int flags, void* stream);
 size_t fa_workspace_bytes_circulant2d_bwd(int64_t X, int64_t Y, int64_t B);
+/* workspace that also admits the tcgen05 backward (16-bit, d = dv in {64,128}, X % 64 == 0); with the smaller amount
+ * above fa_circulant2d_bwd runs its exact fp32 kernels */
+size_t fa_workspace_bytes_circulant2d_bwd_ex(int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags);
 int fa_circulant2d_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                        const float* l, const float* m, void* dq, void* dk, void* dv_out,
                        int64_t X, int64_t Y, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags,

@@ -540,7 +540,7 @@ def test_circulant2d_fwd_tc(X, Y, B, W, dtype):
     walks W key rows x the 64-key tiles of a row, band edges and the wrap round the image row masked in registers.
     2e-3 against the oracle (direct product of the 1-D key set); X = 64 exercises the band wrapping inside one tile,
     X = 128 the all-tiles-of-the-row case, X >= 192 distinct tiles.  The backward (exact fp32 kernels) then takes
-    the (O, l, m) the tcgen05 forward produced."""
+    the (O, l, m) the tcgen05 forward produced.  Also d = 128 below (backward on tcgen05, forward exact fp32)."""
     d = 64
     q, k, v, g = (randn_np((X, Y, d, B), s, dtype) for s in range(4))
     O0, l0, m0 = fo.circulant2d_fa(*(t.astype(np.float64) for t in (q, k, v)), W)
@@ -552,8 +552,27 @@ def test_circulant2d_fwd_tc(X, Y, B, W, dtype):
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
     want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
     got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
+    assert fa.last_path() == "tc"                       # the 1-D circulant tcgen05 backward kernels walking W image rows
     for a, b_ in zip(got, want):
         assert rel_err(to_np(a), b_, dtype) < 4e-3      # D = rowsum(dO o O) from the 16-bit O, P from the 16-bit-compute (l, m)
+    simt = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W, flags=fa.FA_FLAG_FORCE_SIMT)
+    assert fa.last_path() == "simt"
+    for a, b_ in zip(got, simt):                        # same inputs incl. the stored (O, l, m): the two families agree to 2e-3
+        assert rel_err(to_np(a), to_np(b_).astype(np.float64), dtype, want_rounded=True) < 2e-3
+
+
+def test_circulant2d_bwd_tc_d128():
+    """d = 128: the forward runs the exact fp32 kernel (the band kernel is d = 64), the backward the tcgen05 kernels."""
+    X, Y, d, B, W, dtype = 128, 6, 128, 2, 5, BF16
+    q, k, v, g = (randn_np((X, Y, d, B), s, dtype) for s in range(4))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    O, l, m = fa.circulant_fa(Q, K, V, W)
+    assert fa.last_path() == "simt"
+    got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
+    assert fa.last_path() == "tc"
+    want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < 4e-3
 
 
 def test_circulant2d_rejects_bad_window():
