@@ -210,11 +210,11 @@ int fa_circulant2d_fwd(const void* q, const void* k, const void* v, void* o, flo
   if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
   if ((rc = device_ok())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // 16-bit, d = dv = 64, X % 64 == 0: the tcgen05 band kernel walking W key rows (fa_tc_band.cu)
+  // 16-bit, d = dv in {64, 128}, X % 64 == 0: the tcgen05 band kernel walking W key rows (fa_tc_band.cu)
   const bool aligned = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   if (!(flags & FA_FLAG_FORCE_SIMT) && aligned && tc_band2d_supported(X, Y, d, dv, B, W, dtype)) {
     set_path("tc");
-    return tc_band2d_fwd(q, k, v, o, l, m, X, Y, B, W, dtype, st);
+    return tc_band2d_fwd(q, k, v, o, l, m, X, Y, d, B, W, dtype, st);
   }
   set_path("simt");
   if (dtype == FA_F32) return fwd_t<float>(q, k, v, o, l, m, g, st);

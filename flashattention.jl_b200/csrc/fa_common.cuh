@@ -143,10 +143,10 @@ bool tc_fwd_supported(const Geo& g, int dtype);
 int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
 // compact three-CTAs-per-SM forward for short key loops (circulant, d = dv = 64); dispatched from tc_fwd
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
-// the same kernel for the 2-D periodic neighbourhood (fa_circulant2d_fwd): 16-bit, d = dv = 64, X % 64 == 0
+// the same kernel for the 2-D periodic neighbourhood (fa_circulant2d_fwd): 16-bit, d = dv in {64, 128}, X % 64 == 0
 bool tc_band2d_supported(long long X, long long Y, long long d, long long dv, long long B, long long W, int dtype);
 int tc_band2d_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
-                  long long X, long long Y, long long B, long long W, int dtype, cudaStream_t st);
+                  long long X, long long Y, long long d, long long B, long long W, int dtype, cudaStream_t st);
 // tensor-core backward (two deterministic kernels: key-owner dK/dV, query-owner dQ); same coverage
 bool tc_bwd_supported(const Geo& g, int dtype);
 size_t tc_bwd_workspace_bytes(const Geo& g, int dtype, int flags);

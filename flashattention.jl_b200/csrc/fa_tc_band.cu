@@ -36,14 +36,16 @@ namespace {
 
 using namespace ptx;
 
-constexpr int BN = 64, D = 64;
+constexpr int BN = 64;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
-template <int CTAS> struct BandCfg {
+// D = 64: CTAS = 4 (default) or 3.  D = 128 (2-D neighbourhood only): CTAS = 2 -- S 64 + O 128 = 192 -> 256 TMEM columns,
+// Q 32 KB + 2-deep K/V rings of 16 KB tiles = 96 KB, 128 launch registers (misc 64, softmax 192, one-pass softmax).
+template <int CTAS, int D> struct BandCfg {
   static constexpr int THREADS = 256, CTAS_PER_SM = CTAS;
-  static constexpr int STAGES = CTAS == 4 ? 2 : 3;
+  static constexpr int STAGES = CTAS == 3 ? 3 : 2;
   static constexpr int BOX_BYTES = 64 * D * 2, QTILE_BYTES = 2 * BOX_BYTES;
   static constexpr int OFF_Q = 0, OFF_K = QTILE_BYTES, OFF_V = OFF_K + STAGES * BOX_BYTES, OFF_BAR = OFF_V + STAGES * BOX_BYTES;
   static constexpr int BAR_QFULL = 0, BAR_KFULL = 1, BAR_KEMPTY = BAR_KFULL + STAGES, BAR_VFULL = BAR_KEMPTY + STAGES,
@@ -51,7 +53,7 @@ template <int CTAS> struct BandCfg {
                        BAR_OFINAL = BAR_PFULL + 1, NUM_BARS = BAR_OFINAL + 1;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;
-  static constexpr int TMEM_COLS = 128, COL_S = 0, COL_O = 64;
+  static constexpr int TMEM_COLS = D == 64 ? 128 : 256, COL_S = 0, COL_O = 64;
   static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory for CTAS CTAs per SM");
   static_assert(CTAS_PER_SM * TMEM_COLS <= 512, "TMEM");
 };
@@ -112,11 +114,11 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int FMT, int CTAS, int TD>
-__global__ void __launch_bounds__(BandCfg<CTAS>::THREADS, BandCfg<CTAS>::CTAS_PER_SM)
+template <int FMT, int CTAS, int TD, int D>
+__global__ void __launch_bounds__(BandCfg<CTAS, D>::THREADS, BandCfg<CTAS, D>::CTAS_PER_SM)
 tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                const __grid_constant__ CUtensorMap tmv, const BandParams prm) {
-  using C = BandCfg<CTAS>;
+  using C = BandCfg<CTAS, D>;
   constexpr bool TWO_PASS = CTAS == 4;   // 96-register softmax threads hold one 32-column chunk at a time
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -173,7 +175,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   };
 
   if (warp < 4) {
-    if (CTAS == 4) setmaxnreg_dec<32>(); else setmaxnreg_dec<40>();
+    if (CTAS == 4) setmaxnreg_dec<32>(); else if (CTAS == 3) setmaxnreg_dec<40>(); else setmaxnreg_dec<64>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
       mbar_arrive_expect_tx(bar(C::BAR_QFULL), C::QTILE_BYTES);
@@ -253,7 +255,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     }
   } else {
     // -------------------------------------------------------------- softmax: thread == query row
-    if (CTAS == 4) setmaxnreg_inc<96>(); else setmaxnreg_inc<120>();
+    if (CTAS == 4) setmaxnreg_inc<96>(); else if (CTAS == 3) setmaxnreg_inc<120>(); else setmaxnreg_inc<192>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + C::COL_S, tO = tmem_base + lane_addr + C::COL_O;
@@ -497,9 +499,9 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int FMT, int CTAS, int TD>
+template <int FMT, int CTAS, int TD, int D = 64>
 int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int X = 0, int Y = 0) {
-  using C = BandCfg<CTAS>;
+  using C = BandCfg<CTAS, D>;
   CUtensorMap tmq, tmk, tmv;
   int rc;
   if ((rc = make_tmap_public(&tmq, a.q, dtype, g.N, D, g.B))) return rc;
@@ -514,7 +516,7 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 #ifdef FA_TRACE
   { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
 #endif
-  auto kern = tc_band_kernel<FMT, CTAS, TD>;
+  auto kern = tc_band_kernel<FMT, CTAS, TD, D>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const dim3 grid(TD ? (unsigned)(((X + 127) / 128) * Y) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
@@ -534,21 +536,23 @@ int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
 // 2-D periodic neighbourhood attention on (X, Y, 64, B), 16-bit: the same kernel walking W key rows
 bool tc_band2d_supported(long long X, long long Y, long long d, long long dv, long long B, long long W, int dtype) {
   if (dtype != FA_BF16 && dtype != FA_F16) return false;
-  if (d != 64 || dv != 64 || X % 64 != 0 || X <= 0 || Y <= 0 || W <= 0 || W > X || W > Y || W > 64) return false;
+  if (d != dv || (d != 64 && d != 128) || X % 64 != 0 || X <= 0 || Y <= 0 || W <= 0 || W > X || W > Y || W > 64) return false;
   if (B > 65535 || X * Y > 0x3fffffffLL || ((X + 127) / 128) * Y > 0x7fffffffLL) return false;
   return true;
 }
 
 int tc_band2d_fwd(const void* q, const void* k, const void* v, void* o, float* l, float* m,
-                  long long X, long long Y, long long B, long long W, int dtype, cudaStream_t st) {
+                  long long X, long long Y, long long d, long long B, long long W, int dtype, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) {
     set_error("tc_band2d_fwd: q/k/v must be 16-byte aligned"); return FA_ERR_INVALID;
   }
   Geo g;
   memset(&g, 0, sizeof(g));
-  g.mode = MODE_CIRCULANT; g.d = 64; g.dv = 64; g.N = X * Y; g.B = B; g.W = (int)W; g.p = (int)((W - 1) / 2);
-  g.tau = 1.0f / sqrtf(64.f);
+  g.mode = MODE_CIRCULANT; g.d = (int)d; g.dv = (int)d; g.N = X * Y; g.B = B; g.W = (int)W; g.p = (int)((W - 1) / 2);
+  g.tau = 1.0f / sqrtf((float)d);
   FwdArgs a{q, k, v, o, nullptr, l, m};
+  if (d == 128)
+    return dtype == FA_BF16 ? launch_band<1, 2, 1, 128>(g, a, dtype, st, (int)X, (int)Y) : launch_band<0, 2, 1, 128>(g, a, dtype, st, (int)X, (int)Y);
   return dtype == FA_BF16 ? launch_band<1, 4, 1>(g, a, dtype, st, (int)X, (int)Y) : launch_band<0, 4, 1>(g, a, dtype, st, (int)X, (int)Y);
 }
 

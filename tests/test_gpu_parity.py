@@ -561,13 +561,17 @@ def test_circulant2d_fwd_tc(X, Y, B, W, dtype):
         assert rel_err(to_np(a), to_np(b_).astype(np.float64), dtype, want_rounded=True) < 2e-3
 
 
-def test_circulant2d_bwd_tc_d128():
-    """d = 128: the forward runs the exact fp32 kernel (the band kernel is d = 64), the backward the tcgen05 kernels."""
-    X, Y, d, B, W, dtype = 128, 6, 128, 2, 5, BF16
+@pytest.mark.parametrize("X,Y,B,W", [(128, 6, 2, 5), (64, 7, 1, 7), (192, 16, 1, 16)])
+def test_circulant2d_fwd_bwd_tc_d128(X, Y, B, W):
+    """d = 128: the band kernel's two-CTA configuration (forward) and the tcgen05 circulant backward kernels."""
+    d, dtype = 128, BF16
     q, k, v, g = (randn_np((X, Y, d, B), s, dtype) for s in range(4))
     Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    O0, l0, m0 = fo.circulant2d_fa(*(t.astype(np.float64) for t in (q, k, v)), W)
     O, l, m = fa.circulant_fa(Q, K, V, W)
-    assert fa.last_path() == "simt"
+    assert fa.last_path() == "tc"
+    assert rel_err(to_np(O), O0, dtype) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
     got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
     assert fa.last_path() == "tc"
     want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
