@@ -911,6 +911,9 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
     // d = 64: the compact band kernel (three CTAs per SM, fa_tc_band.cu); FA_BAND=0 keeps the two-CTA variant below
     static const int band = [] { const char* e = getenv("FA_BAND"); return e ? atoi(e) : 1; }();
     if (band && g.d == 64 && !a.o_f32) return tc_band_fwd(g, a, dtype, st);
+    // d = 128: the band kernel's two-CTA configuration (N = 16384, W = 255, B = 256: 1.34 vs 2.19 ms); FA_BAND128=0 disables
+    static const int band128 = [] { const char* e = getenv("FA_BAND128"); return e ? atoi(e) : 1; }();
+    if (band && band128 && g.d == 128 && !a.o_f32) return tc_band_fwd(g, a, dtype, st);
     if (g.d == 128) return fmt ? launch_tc<128, 1, 1>(g, a, dtype, st) : launch_tc<128, 0, 1>(g, a, dtype, st);
     return fmt ? launch_tc<64, 1, 1>(g, a, dtype, st) : launch_tc<64, 0, 1>(g, a, dtype, st);
   }
