@@ -62,6 +62,7 @@ struct BandParams {
   void* o;
   float *l, *m;
   int N, W, p;
+  int dense;             // dense attention (d = 64 default, FA_DENSE_BAND): every key tile once, no band; last tile masked at N
   int X, Y;              // TD (2-D periodic neighbourhood): image extents, N = X * Y, tokens x-fastest
   float scale_log2;
   long long* trace;      // FA_TRACE builds: one CTA in the middle of the grid records clock64() per event
@@ -159,13 +160,13 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   // TD: the keys of (x, y) are (mod(x - p + s, X), mod(y - p + t, Y)), s, t in [0, W) -- the direct product of the
   // 1-D key set (src/utils.jl:6-17).  Steps = W key rows x the nx 64-key tiles of a row that meet the x band of the
   // query tile (all X / 64 tiles of the row, once each, when the band wraps round the whole row).
-  const int kbase = TD ? fdiv(x0 - prm.p, BN) * BN : fdiv(q0 - prm.p, BN) * BN;
+  const int kbase = prm.dense ? 0 : (TD ? fdiv(x0 - prm.p, BN) * BN : fdiv(q0 - prm.p, BN) * BN);
   int nx = 1, kxb = kbase;
   if (TD) {
     nx = fdiv(x0 + tq - 1 - prm.p + prm.W - 1 - kbase, BN) + 1;
     if (nx * BN >= prm.X) { nx = prm.X / BN; kxb = 0; }
   }
-  const int nj = TD ? prm.W * nx : fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1;
+  const int nj = prm.dense ? (prm.N + BN - 1) / BN : (TD ? prm.W * nx : fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1);
   // token of the first key of step j (TD: row (yq - p + t) mod Y, x tile (kxb + 64 jx) mod X)
   auto key_tile = [&](int j, int& kxs) {
     if (!TD) { kxs = 0; return (int)pmod(kbase + BN * j, prm.N); }
@@ -364,6 +365,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
         lo2 = lo - prm.X; hi2 = lo2 + prm.W;
       } else {
         lo = lo0 - BN * j; hi = lo + prm.W;
+        if (prm.dense) { lo = 0; hi = prm.N - BN * j; }
       }
       const bool two = TD && __any_sync(0xffffffffu, hi2 > 0);       // warp-uniform: some lane's band wraps into this tile
       // Each 32-column chunk is classified per warp (the band edge is a diagonal: it crosses ~32 columns over a
@@ -511,6 +513,7 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.W = g.W; prm.p = g.p;
   prm.X = X; prm.Y = Y;
+  prm.dense = g.mode == MODE_DENSE ? 1 : 0;
   prm.scale_log2 = g.tau * LOG2E;
   prm.trace = nullptr;
 #ifdef FA_TRACE
