@@ -87,10 +87,9 @@ struct BandParams {
 
 // FA_BAND_SPIN: poll the two hand-off barriers of the per-step chain (S ready -> softmax, P ready -> issuer) with
 // the non-suspending test_wait instead of try_wait (which may park the thread for a system-dependent time)
-// FA_BAND_EMU: column pairs (of the 4 per block of 8) whose exponentials are evaluated on the FMA pipe instead of MUFU
-#ifndef FA_BAND_EMU
-#define FA_BAND_EMU 0
-#endif
+// EMU (template): column pairs (of the 4 per block of 8) whose exponentials are evaluated on the FMA pipe instead of
+// MUFU.  Dense d = 64 is MUFU-bound (512 clk of ex2 vs 492 clk of MMA per 128 x 64 tile): EMU = 1 gives 2.74 -> 2.63 ms at
+// N = 8192, B = 128; EMU = 2 is slower (2.87); the latency-bound band configurations do not gain (1.426 vs 1.4215 ms).
 #ifndef FA_BAND_SPIN
 #define FA_BAND_SPIN 0
 #endif
@@ -115,7 +114,7 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int FMT, int CTAS, int TD, int D>
+template <int FMT, int CTAS, int TD, int D, int EMU>
 __global__ void __launch_bounds__(BandCfg<CTAS, D>::THREADS, BandCfg<CTAS, D>::CTAS_PER_SM)
 tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
                const __grid_constant__ CUtensorMap tmv, const BandParams prm) {
@@ -321,7 +320,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
           x[u] = __ffma2_rn(make_float2(__uint_as_float(sc[e0 + 2 * u]), __uint_as_float(sc[e0 + 2 * u + 1])), scale2, negm2);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (u >= 4 - FA_BAND_EMU) {
+          if (u >= 4 - EMU) {
             // exponential on the FMA pipe (Cody-Waite split + cubic, rel. error 9e-5 << 16-bit rounding of P)
             float2 t = x[u];
             t.x = fmaxf(t.x, -126.f); t.y = fmaxf(t.y, -126.f);
@@ -501,7 +500,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int FMT, int CTAS, int TD, int D = 64>
+template <int FMT, int CTAS, int TD, int D = 64, int EMU = 0>
 int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int X = 0, int Y = 0) {
   using C = BandCfg<CTAS, D>;
   CUtensorMap tmq, tmk, tmv;
@@ -519,7 +518,7 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 #ifdef FA_TRACE
   { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
 #endif
-  auto kern = tc_band_kernel<FMT, CTAS, TD, D>;
+  auto kern = tc_band_kernel<FMT, CTAS, TD, D, EMU>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const dim3 grid(TD ? (unsigned)(((X + 127) / 128) * Y) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
@@ -533,6 +532,7 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   if (g.d == 128) return dtype == FA_BF16 ? launch_band<1, 2, 0, 128>(g, a, dtype, st) : launch_band<0, 2, 0, 128>(g, a, dtype, st);
   static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
+  if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 4, 0, 64, 1>(g, a, dtype, st) : launch_band<0, 4, 0, 64, 1>(g, a, dtype, st);
   if (ctas != 3) return dtype == FA_BF16 ? launch_band<1, 4, 0>(g, a, dtype, st) : launch_band<0, 4, 0>(g, a, dtype, st);
   return dtype == FA_BF16 ? launch_band<1, 3, 0>(g, a, dtype, st) : launch_band<0, 3, 0>(g, a, dtype, st);
 }

@@ -917,8 +917,8 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
     if (g.d == 128) return fmt ? launch_tc<128, 1, 1>(g, a, dtype, st) : launch_tc<128, 0, 1>(g, a, dtype, st);
     return fmt ? launch_tc<64, 1, 1>(g, a, dtype, st) : launch_tc<64, 0, 1>(g, a, dtype, st);
   }
-  // dense, d = 64: the band kernel (serial CTAs, four per SM) beats the pair kernel -- N = 8192, B = 128: 2.74 vs 3.28 ms
-  // (802 vs 670 TFLOP/s); at d = 128 the pair kernel wins (1.79 vs 2.09 ms at B = 64).  FA_DENSE_BAND=0 / 2 = never / always.
+  // dense, d = 64: the band kernel (serial CTAs, four per SM) beats the pair kernel -- N = 8192, B = 128: 2.63 vs 3.28 ms
+  // (836 vs 670 TFLOP/s; a quarter of the exponentials on the FMA pipe); at d = 128 the pair kernel wins (1.79 vs 2.09 ms at B = 64).  FA_DENSE_BAND=0 / 2 = never / always.
   static const int dense_band = [] { const char* e = getenv("FA_DENSE_BAND"); return e ? atoi(e) : 1; }();
   if (g.mode == MODE_DENSE && !a.o_f32 && ((dense_band == 1 && g.d == 64) || dense_band == 2)) return tc_band_fwd(g, a, dtype, st);
   static const int split = [] { const char* e = getenv("FA_FWD_SPLIT"); return e ? atoi(e) : 1; }();
