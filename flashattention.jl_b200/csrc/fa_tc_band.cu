@@ -62,7 +62,6 @@ struct BandParams {
   void* o;
   float *l, *m;
   int N, W, p;
-  int dense;             // dense attention (d = 64 default, FA_DENSE_BAND): every key tile once, no band; last tile masked at N
   int X, Y;              // TD (2-D periodic neighbourhood): image extents, N = X * Y, tokens x-fastest
   float scale_log2;
   long long* trace;      // FA_TRACE builds: one CTA in the middle of the grid records clock64() per event
@@ -114,6 +113,7 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// TD: 0 = 1-D periodic band (circulant_fa!), 1 = 2-D periodic neighbourhood, 2 = dense (every key tile once)
 template <int FMT, int CTAS, int TD, int D, int EMU>
 __global__ void __launch_bounds__(BandCfg<CTAS, D>::THREADS, BandCfg<CTAS, D>::CTAS_PER_SM)
 tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
@@ -129,11 +129,11 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   // 1-D: query tile = 128 consecutive tokens.  TD: query tile = up to 128 consecutive x of ONE image row yq
   // (tokens are x-fastest, X % 64 == 0), blockIdx.x = row * tiles_per_row + tile.
   const int b = blockIdx.y;
-  const int tpr = TD ? (prm.X + 127) / 128 : 1;
-  const int yq = TD ? (int)(blockIdx.x / tpr) : 0;
-  const int x0 = TD ? (int)(blockIdx.x % tpr) * 128 : 0;
-  const int tq = TD ? (prm.X - x0 < 128 ? prm.X - x0 : 128) : 128;
-  const int q0 = TD ? yq * prm.X + x0 : blockIdx.x * 128;
+  const int tpr = TD == 1 ? (prm.X + 127) / 128 : 1;
+  const int yq = TD == 1 ? (int)(blockIdx.x / tpr) : 0;
+  const int x0 = TD == 1 ? (int)(blockIdx.x % tpr) * 128 : 0;
+  const int tq = TD == 1 ? (prm.X - x0 < 128 ? prm.X - x0 : 128) : 128;
+  const int q0 = TD == 1 ? yq * prm.X + x0 : blockIdx.x * 128;
   if (warp == 1) BTRACE(0, 15, 0);                         // kernel entry
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv); }
@@ -159,16 +159,16 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   // TD: the keys of (x, y) are (mod(x - p + s, X), mod(y - p + t, Y)), s, t in [0, W) -- the direct product of the
   // 1-D key set (src/utils.jl:6-17).  Steps = W key rows x the nx 64-key tiles of a row that meet the x band of the
   // query tile (all X / 64 tiles of the row, once each, when the band wraps round the whole row).
-  const int kbase = prm.dense ? 0 : (TD ? fdiv(x0 - prm.p, BN) * BN : fdiv(q0 - prm.p, BN) * BN);
+  const int kbase = TD == 2 ? 0 : (TD == 1 ? fdiv(x0 - prm.p, BN) * BN : fdiv(q0 - prm.p, BN) * BN);
   int nx = 1, kxb = kbase;
-  if (TD) {
+  if (TD == 1) {
     nx = fdiv(x0 + tq - 1 - prm.p + prm.W - 1 - kbase, BN) + 1;
     if (nx * BN >= prm.X) { nx = prm.X / BN; kxb = 0; }
   }
-  const int nj = prm.dense ? (prm.N + BN - 1) / BN : (TD ? prm.W * nx : fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1);
+  const int nj = TD == 2 ? (prm.N + BN - 1) / BN : (TD == 1 ? prm.W * nx : fdiv(q0 + 127 - prm.p + prm.W - 1 - kbase, BN) + 1);
   // token of the first key of step j (TD: row (yq - p + t) mod Y, x tile (kxb + 64 jx) mod X)
   auto key_tile = [&](int j, int& kxs) {
-    if (!TD) { kxs = 0; return (int)pmod(kbase + BN * j, prm.N); }
+    if (TD != 1) { kxs = 0; return (int)pmod(kbase + BN * j, prm.N); }
     const int t = j / nx, jx = j - t * nx;
     kxs = (int)pmod(kxb + BN * jx, prm.X);
     return (int)pmod(yq - prm.p + t, prm.Y) * prm.X + kxs;
@@ -357,16 +357,16 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
       // valid columns of this key tile for this row: [lo, hi), and for TD also [lo2, hi2) = the same band one image
       // row length to the left (periodic in x): (c - a) mod X < W with a = (qx - p - tile start) mod X
       int lo, hi, lo2 = 0, hi2 = 0;
-      if (TD) {
+      if (TD == 1) {
         int kxs;
         key_tile(j, kxs);
         lo = (int)pmod(qx - prm.p - kxs, prm.X); hi = lo + prm.W;
         lo2 = lo - prm.X; hi2 = lo2 + prm.W;
       } else {
         lo = lo0 - BN * j; hi = lo + prm.W;
-        if (prm.dense) { lo = 0; hi = prm.N - BN * j; }
+        if (TD == 2) { lo = 0; hi = prm.N - BN * j; }
       }
-      const bool two = TD && __any_sync(0xffffffffu, hi2 > 0);       // warp-uniform: some lane's band wraps into this tile
+      const bool two = TD == 1 && __any_sync(0xffffffffu, hi2 > 0);       // warp-uniform: some lane's band wraps into this tile
       // Each 32-column chunk is classified per warp (the band edge is a diagonal: it crosses ~32 columns over a
       // warp's 32 rows): 1 = inside the band of every lane (no predicates), 2 = outside for every lane (P = 0: S is
       // not read, no exponentials), 0 = mixed (per-element select).
@@ -374,7 +374,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         bool in = lo <= 32 * c && 32 * c + 32 <= hi, out = hi <= 32 * c || lo >= 32 * c + 32;
-        if (TD) {
+        if (TD == 1) {
           const int c1 = min(hi, 32 * c + 32) - max(lo, 32 * c), c2 = min(hi2, 32 * c + 32) - max(lo2, 32 * c);
           const int cnt = (c1 > 0 ? c1 : 0) + (c2 > 0 ? c2 : 0);
           in = cnt == 32; out = cnt == 0;
@@ -471,7 +471,7 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     if (warp == 4) BTRACE(1, 15, 0);                        // all MMAs done
     tc_fence_after();
     const float inv_l = 1.f / l_run;
-    const bool in_range = TD ? row < tq : qi < prm.N;
+    const bool in_range = TD == 1 ? row < tq : qi < prm.N;
     unsigned short* ob = static_cast<unsigned short*>(prm.o) + (size_t)b * D * prm.N + qi;
 #pragma unroll 1
     for (int c = 0; c < D / 32; ++c) {
@@ -512,7 +512,6 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.W = g.W; prm.p = g.p;
   prm.X = X; prm.Y = Y;
-  prm.dense = g.mode == MODE_DENSE ? 1 : 0;
   prm.scale_log2 = g.tau * LOG2E;
   prm.trace = nullptr;
 #ifdef FA_TRACE
@@ -520,7 +519,7 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 #endif
   auto kern = tc_band_kernel<FMT, CTAS, TD, D, EMU>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const dim3 grid(TD ? (unsigned)(((X + 127) / 128) * Y) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
+  const dim3 grid(TD == 1 ? (unsigned)(((X + 127) / 128) * Y) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tmq, tmk, tmv, prm);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
@@ -530,9 +529,13 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 
 // circulant, d = dv in {64, 128}, 16-bit output, tile-aligned wrap-around (N % 64 == 0) -- checked by the caller (tc_fwd)
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
-  if (g.d == 128) return dtype == FA_BF16 ? launch_band<1, 2, 0, 128>(g, a, dtype, st) : launch_band<0, 2, 0, 128>(g, a, dtype, st);
+  if (g.d == 128) {
+    if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 2, 2, 128>(g, a, dtype, st) : launch_band<0, 2, 2, 128>(g, a, dtype, st);
+    return dtype == FA_BF16 ? launch_band<1, 2, 0, 128>(g, a, dtype, st) : launch_band<0, 2, 0, 128>(g, a, dtype, st);
+  }
   static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
-  if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 4, 0, 64, 1>(g, a, dtype, st) : launch_band<0, 4, 0, 64, 1>(g, a, dtype, st);
+  // dense (TD = 2): every key tile once, no band, the last tile masked at N; a quarter of the exponentials on the FMA pipe
+  if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 4, 2, 64, 1>(g, a, dtype, st) : launch_band<0, 4, 2, 64, 1>(g, a, dtype, st);
   if (ctas != 3) return dtype == FA_BF16 ? launch_band<1, 4, 0>(g, a, dtype, st) : launch_band<0, 4, 0>(g, a, dtype, st);
   return dtype == FA_BF16 ? launch_band<1, 3, 0>(g, a, dtype, st) : launch_band<0, 3, 0>(g, a, dtype, st);
 }
