@@ -1,5 +1,5 @@
 // fa_tc_band.cu -- compact tcgen05 / TMEM / TMA forward for SHORT key loops: circulant_fa! (reference
-// src/circulant.jl:9-118) with d == dv == 64, where a 128-query tile meets only (128 + W) / 64 key tiles.
+// src/circulant.jl:9-118), described for d == dv == 64, where a 128-query tile meets only (128 + W) / 64 key tiles.
 //
 // Why a second forward kernel: the pair kernel of fa_tc_fwd.cu is built for long key loops (S double
 // buffered, QK two steps ahead, 200-register softmax threads) and fits 2 CTAs = 2 query tiles per SM.  With
@@ -18,9 +18,18 @@
 // with three CTAs 1.811 ms, with four 1.645 ms; one-sided masks written back once 1.512 ms; chunk 0 kept in
 // registers between the passes and PV(j) + QK(j+1) handed to the pipe by one elected lane 1.425 ms
 // (profiles/r1t_band_kernel.md).
-// Per step the CTA is serial (QK(j) -> softmax(j) -> PV(j) -> QK(j+1)); the other two CTAs fill the gaps.
+// Per step the CTA is serial (QK(j) -> softmax(j) -> PV(j) -> QK(j+1)); the other CTAs of the SM fill the gaps.
 // Layout, descriptors and masking are those of fa_tc_fwd.cu (token-contiguous [B][d][N], SWIZZLE_128B boxes of
-// 64 tokens x 64 channels, MN-major Q/K for S = Q K^T, K-major V for O = P V).
+// 64 tokens x d channels, MN-major Q/K for S = Q K^T, K-major V for O = P V).
+//
+// The same kernel also serves (template parameters TD, D, EMU; all measured in profiles/r1t_band_kernel.md):
+//   * d = 128 (D): two CTAs per SM, S 64 + O 128 = 192 TMEM columns, one-pass softmax at 192 registers -- circulant
+//     d = 128: 1.34 vs 2.19 ms for the pair kernel;
+//   * the 2-D periodic neighbourhood of fa_circulant2d_fwd (TD = 1): a query tile is up to 128 consecutive x of one
+//     image row, the steps are the W key rows x the 64-key tiles of a row that meet the x band, the mask
+//     (c - a) mod X < W is one or two column intervals;
+//   * dense attention at d = 64 (TD = 2): every key tile once, the last one masked at N; MUFU-bound there, so a
+//     quarter of the exponentials go to the FMA pipe (EMU = 1): 2.60 vs 3.28 ms at N = 8192, B = 128.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
