@@ -428,6 +428,16 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        // band kernels: a 32-column chunk outside the band of every row of this warp has P = dS = 0 -- nothing to read
+        // or exponentiate (2-D neighbourhood: W of the 64 columns of a step are inside; 1-D: the edge tiles)
+        if (circ) {
+          const bool outside = (hi <= 32 * c || lo >= 32 * c + 32) && (hi2 <= 32 * c || lo2 >= 32 * c + 32);
+          if (__all_sync(0xffffffffu, outside)) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { pk[16 * c + e] = 0u; dk[16 * c + e] = 0u; }
+            continue;
+          }
+        }
         uint32_t sc[32], dp[32];
         tmem_ld32(tT1 + 32 * c, sc);
         tmem_ld32(tT2 + 32 * c, dp);
