@@ -589,7 +589,14 @@ struct WinBwdParams {
   WinMap mp;
   long long ngroups, nwin;
   float scale_log2, tau;
+  long long* trace;          // FA_TRACE builds: CTA 1 records clock64() per phase of its first 16 iterations
 };
+
+#ifdef FA_TRACE
+#define BTR(ev) do { if (prm.trace && blockIdx.x == 1 && tid == 0 && bit < 16) prm.trace[bit * 8 + (ev)] = clock64(); } while (0)
+#else
+#define BTR(ev) do {} while (0)
+#endif
 
 __device__ __forceinline__ float pow2_norm_scale(uint32_t amax_bits) {   // s = 2^k with amax * s in [4, 8)
   const int e = (int)((amax_bits >> 7) & 0xff);      // bf16 biased exponent (bits are |x| of a bf16 value)
@@ -668,13 +675,17 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
   };
 
   uint32_t pa = 0, pb = 0;
+  int bit = -1;                                          // iteration counter (trace builds)
   for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x) {
+    ++bit;
+    BTR(6);                                              // iteration start
     const long long gw0 = grp * mp.nwc;
     if (tid < 4) samax[tid] = 0;
     build_wininfo(g, mp, gw0, prm.nwin, wininfo, tid);
     __syncthreads();
     build_table(g, mp, wininfo, D, tsrc, trow, tid, 128, rowtok);
     __syncthreads();
+    BTR(0);                                              // tables built (iteration start + tables)
 
     // ---- A: gather q, k, v, dy
     {
@@ -697,6 +708,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
       }
     }
     __syncthreads();
+    BTR(1);                                              // gather done
     float sq = 1.f, sk = 1.f, sv = 1.f, sg = 1.f;
     if (INBF) {
       // per-tile power-of-two scales, then bf16 -> fp16 in place (exact for everything within 2^-17 of the max)
@@ -717,6 +729,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
     }
     fence_proxy_async();
     __syncthreads();
+    BTR(2);                                              // re-encode done
 
     // ---- B: S = Q K^T, dP = dY V^T;  thread == query row
     issue_T(sQ, sK, sG, sV, bar_a);
@@ -770,6 +783,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
     tmem_wait_st();
     tc_fence_before();
     __syncthreads();
+    BTR(3);                                              // pass B element-wise done
     if (warp == 0) {                     // dQ = dS K  (accumulator over the dead S columns)
       tc_fence_after();
       if (elect_one()) { issue_acc(C::COL_DQ, C::COL_T2, sK); tc_commit(bar_b); }
@@ -791,6 +805,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
     }
     tc_fence_before();
     __syncthreads();
+    BTR(4);                                              // dQ MMA issued / pass B done
 
     // ---- C: S^T = K Q^T, dP^T = V dY^T;  thread == key row, per-column (query) stats from smem
     issue_T(sK, sQ, sV, sG, bar_a);
@@ -820,6 +835,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
     tmem_wait_st();
     tc_fence_before();
     __syncthreads();
+    BTR(5);                                              // pass C element-wise done
     if (warp == 0) {                     // dV = P^T dY,  dK = dS^T Q
       tc_fence_after();
       if (elect_one()) { issue_acc(C::COL_DV, C::COL_T1, sG); issue_acc(C::COL_DK, C::COL_T2, sQ); tc_commit(bar_b); }
@@ -885,6 +901,7 @@ tc_win_bwd_kernel(const WinBwdParams prm) {
     }
     tc_fence_before();
     __syncthreads();
+    BTR(7);                                              // scatter of dQ, dV, dK done
   }
 
   tc_fence_before();
@@ -1011,6 +1028,10 @@ int launch_win_bwd(const Geo& g, const BwdArgs& a, cudaStream_t st) {
   prm.nwin = g.L * g.B;
   prm.ngroups = (prm.nwin + prm.mp.nwc - 1) / prm.mp.nwc;
   prm.scale_log2 = g.tau * LOG2E; prm.tau = g.tau;
+  prm.trace = nullptr;
+#ifdef FA_TRACE
+  { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
   auto kern = tc_win_bwd_kernel<D, INBF>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int dev = 0, sms = 148;

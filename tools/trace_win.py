@@ -16,6 +16,21 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = buf.cpu().reshape(16, 8)
 names = ["tables", "gather", "QK", "softmax", "PV", "stage O", "scatter"]
+mode = sys.argv[2] if len(sys.argv) > 2 else "fwd"
+if mode == "bwd":
+    g = torch.randn_like(q)
+    y, l, m = fa.windowed_fa(q, k, v, 5, 5, 3)
+    buf.zero_()
+    for _ in range(3):
+        fa.windowed_fa_backward(q, k, v, g, l, m, 5, 5, 3)
+    torch.cuda.synchronize()
+    t = buf.cpu().reshape(16, 8)
+    print("backward per iteration: clk in [tables, gather(4 tensors), re-encode, pass B element-wise, dQ MMA, pass C, stage+scatter x3] | total")
+    for it in range(4, 12):
+        r = [int(x) for x in t[it]]
+        seq = [r[6], r[0], r[1], r[2], r[3], r[4], r[5], r[7]]
+        print("  it", it, [seq[i + 1] - seq[i] for i in range(7)], "|", seq[7] - seq[0])
+    sys.exit(0)
 print("per iteration: clk in", names, "| total")
 for it in range(4, 12):
     r = [int(x) for x in t[it]]
