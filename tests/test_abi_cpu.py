@@ -132,3 +132,23 @@ def test_circulant2d_index_bit_exact():
     import pytest
     with pytest.raises(fa.FaError):
         fa.circulant2d_keys(4, 8, 5)          # W > X would duplicate keys
+
+
+def test_workspace_queries_are_pure_host_functions(fa):
+    """Workspace sizes are computed on the host (no device needed) and ordered as documented in include/fa_sm100a.h:
+    the _ex query of the 2-D neighbourhood backward is never below the basic one, larger exactly where the tcgen05
+    backward applies (16-bit, d = dv in {64, 128}, X % 64 == 0), and equal to it when FORCE_SIMT is set."""
+    L = fa.lib
+    base = L.fa_workspace_bytes_circulant2d_bwd(128, 16, 2)
+    assert base >= 128 * 16 * 2 * 4
+    import torch
+    bf, f32 = fa._DTYPES[torch.bfloat16], fa._DTYPES[torch.float32]
+    assert L.fa_workspace_bytes_circulant2d_bwd_ex(128, 16, 64, 64, 2, 7, bf, 0) > base          # tcgen05 path
+    assert L.fa_workspace_bytes_circulant2d_bwd_ex(128, 16, 64, 64, 2, 7, bf, fa.FA_FLAG_FORCE_SIMT) == base
+    assert L.fa_workspace_bytes_circulant2d_bwd_ex(128, 16, 64, 64, 2, 7, f32, 0) == base        # Float32: exact kernels
+    assert L.fa_workspace_bytes_circulant2d_bwd_ex(100, 16, 64, 64, 2, 7, bf, 0) == L.fa_workspace_bytes_circulant2d_bwd(100, 16, 2)
+    assert L.fa_workspace_bytes_circulant2d_bwd_ex(128, 16, 32, 32, 2, 7, bf, 0) == base         # d = 32: exact kernels
+    # slab backward workspace: the delta buffer of the slab's own windows
+    dims = fa._i64arr((64, 64, 10))
+    assert L.fa_workspace_bytes_windowed_slab_bwd(3, dims, 64, 64, 1, 5, 5, 3, 0, 2) >= 125 * 14 * 14 * 2 * 4
+    assert L.fa_workspace_bytes_windowed_slab_bwd(3, dims, 64, 64, 1, 5, 4, 3, 0, 2) == 0        # overlapping windows: rejected
