@@ -145,24 +145,6 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
   const int q0 = TD == 1 ? yq * prm.X + x0 : blockIdx.x * 128;
   if (warp == 1) BTRACE(0, 15, 0);                         // kernel entry
 
-  if (warp == 0 && lane == 0) { prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv); }
-  if (warp == 1 && lane == 0) {
-    mbar_init(bar(C::BAR_QFULL), 1);
-    for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_KEMPTY + i), 1);
-      mbar_init(bar(C::BAR_VFULL + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), 1);
-    }
-    mbar_init(bar(C::BAR_SFULL), 1); mbar_init(bar(C::BAR_PFULL), 128); mbar_init(bar(C::BAR_OFINAL), 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  if (warp == 1) BTRACE(0, 15, 1);                         // set-up done
-
   // key tiles of this query tile: keys (q - p) .. (q - p + W - 1) for q in [q0, q0 + 128), from the 64-aligned
   // tile at or below q0 - p (src/circulant.jl:61-67: the window of query j starts p keys before it, periodic)
   // TD: the keys of (x, y) are (mod(x - p + s, X), mod(y - p + t, Y)), s, t in [0, W) -- the direct product of the
@@ -183,14 +165,41 @@ tc_band_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ 
     return (int)pmod(yq - prm.p + t, prm.Y) * prm.X + kxs;
   };
 
+  // The producer initialises its own "full" barriers and sends the first round trip (Q, K(0), V(0)) on its way BEFORE the
+  // CTA-wide set-up barrier: TMEM allocation and the other barrier inits overlap the ~1800-clk TMA latency.
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmq); prefetch_tensormap(&tmk); prefetch_tensormap(&tmv);
+    mbar_init(bar(C::BAR_QFULL), 1);
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(bar(C::BAR_KFULL + i), 1); mbar_init(bar(C::BAR_VFULL + i), 1); }
+    fence_barrier_init();
+    mbar_arrive_expect_tx(bar(C::BAR_QFULL), C::QTILE_BYTES);
+    tma_load_3d(sQ, &tmq, bar(C::BAR_QFULL), q0, 0, b);
+    tma_load_3d(sQ + C::BOX_BYTES, &tmq, bar(C::BAR_QFULL), q0 + 64, 0, b);
+    int kxs0;
+    const int tok0 = key_tile(0, kxs0);
+    mbar_arrive_expect_tx(bar(C::BAR_KFULL), C::BOX_BYTES);
+    tma_load_3d(sK, &tmk, bar(C::BAR_KFULL), tok0, 0, b);
+    mbar_arrive_expect_tx(bar(C::BAR_VFULL), C::BOX_BYTES);
+    tma_load_3d(sV, &tmv, bar(C::BAR_VFULL), tok0, 0, b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(bar(C::BAR_KEMPTY + i), 1); mbar_init(bar(C::BAR_VEMPTY + i), 1); }
+    mbar_init(bar(C::BAR_SFULL), 1); mbar_init(bar(C::BAR_PFULL), 128); mbar_init(bar(C::BAR_OFINAL), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 1) BTRACE(0, 15, 1);                         // set-up done
+
   if (warp < 4) {
     if (CTAS == 4) setmaxnreg_dec<32>(); else if (CTAS == 3) setmaxnreg_dec<40>(); else setmaxnreg_dec<64>();
     if (warp == 0 && lane == 0) {
       // ------------------------------------------------------------ TMA producer
-      mbar_arrive_expect_tx(bar(C::BAR_QFULL), C::QTILE_BYTES);
-      tma_load_3d(sQ, &tmq, bar(C::BAR_QFULL), q0, 0, b);
-      tma_load_3d(sQ + C::BOX_BYTES, &tmq, bar(C::BAR_QFULL), q0 + 64, 0, b);
-      for (int j = 0; j < nj; ++j) {
+      for (int j = 1; j < nj; ++j) {                       // step 0 went out before the set-up barrier
         const int s = j % C::STAGES;
         const uint32_t par = ((uint32_t)(j / C::STAGES) & 1u) ^ 1u;
         int kxs_unused;
