@@ -325,3 +325,34 @@ def test_windowed_slabs_reproduce_whole_volume_bitwise(spatial, W, stride, pad, 
     assert eq(torch.cat(ys, dim=ax), y0) and eq(torch.cat(ls, dim=2), l0) and eq(torch.cat(ms, dim=2), m0)
     for acc, want in zip(gs, g0):
         assert eq(torch.cat(acc, dim=ax), want)
+
+
+def test_windowed_slab_plan_random_geometries():
+    """Randomised check of the slab plan (CPU only): for random extents / windows / strides / paddings / rank counts the C
+    plan equals the brute-force oracle, the slabs tile the slowest dim, every window plane is owned exactly once, and each
+    slab's own window geometry (pad_lo, nwin) reproduces the window starts of the whole volume."""
+    import fa_sm100a as fa
+    rng = np.random.default_rng(123)
+    for _ in range(300):
+        nd = int(rng.integers(1, 4))
+        W = int(rng.integers(1, 9))
+        stride = W + int(rng.integers(0, 4))
+        pad = int(rng.integers(0, W))
+        spatial = tuple(int(rng.integers(W, 40)) for _ in range(nd))
+        G = int(rng.integers(1, 9))
+        nw = fo.window_counts(spatial, W, stride, pad)[-1]
+        plans = [fa.windowed_slab_plan(spatial, W, stride, pad, r, G) for r in range(G)]
+        for r, pl in enumerate(plans):
+            assert tuple(pl) == tuple(fo.windowed_slab_plan(spatial, W, stride, pad, r, G)), (spatial, W, stride, pad, G, r)
+        live = [pl for pl in plans if pl.nwin > 0]
+        assert sum(pl.nwin for pl in plans) == nw and live[0].plane_lo == 0 and live[-1].plane_hi == spatial[-1]
+        for a, b in zip(live, live[1:]):
+            assert a.plane_hi == b.plane_lo and a.win_hi == b.win_lo
+        for pl in live:
+            # window w of the slab starts at w * stride - pad_lo in slab coordinates = (win_lo + w) * stride - pad in the volume
+            for w in range(pl.nwin):
+                assert pl.plane_lo + w * stride - pl.pad_lo == (pl.win_lo + w) * stride - pad
+            # every plane the slab's windows read and the volume holds is inside the slab
+            first = pl.win_lo * stride - pad
+            last = (pl.win_hi - 1) * stride - pad + W - 1
+            assert pl.plane_lo <= max(first, 0) and min(last, spatial[-1] - 1) < pl.plane_hi
