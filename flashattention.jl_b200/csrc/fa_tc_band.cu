@@ -547,13 +547,16 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 
 // circulant, d = dv in {64, 128}, 16-bit output, tile-aligned wrap-around (N % 64 == 0) -- checked by the caller (tc_fwd)
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
+  static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
   if (g.d == 128) {
     if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 2, 2, 128>(g, a, dtype, st) : launch_band<0, 2, 2, 128>(g, a, dtype, st);
     return dtype == FA_BF16 ? launch_band<1, 2, 0, 128>(g, a, dtype, st) : launch_band<0, 2, 0, 128>(g, a, dtype, st);
   }
-  static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
   // dense (TD = 2): every key tile once, no band, the last tile masked at N; a quarter of the exponentials on the FMA pipe
-  if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 4, 2, 64, 1>(g, a, dtype, st) : launch_band<0, 4, 2, 64, 1>(g, a, dtype, st);
+  if (g.mode == MODE_DENSE) {
+    if (ctas == 3) return dtype == FA_BF16 ? launch_band<1, 3, 2, 64, 1>(g, a, dtype, st) : launch_band<0, 3, 2, 64, 1>(g, a, dtype, st);
+    return dtype == FA_BF16 ? launch_band<1, 4, 2, 64, 1>(g, a, dtype, st) : launch_band<0, 4, 2, 64, 1>(g, a, dtype, st);
+  }
   if (ctas != 3) return dtype == FA_BF16 ? launch_band<1, 4, 0>(g, a, dtype, st) : launch_band<0, 4, 0>(g, a, dtype, st);
   return dtype == FA_BF16 ? launch_band<1, 3, 0>(g, a, dtype, st) : launch_band<0, 3, 0>(g, a, dtype, st);
 }
