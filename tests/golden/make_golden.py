@@ -41,6 +41,7 @@ CASES = {
     "win1d_n22_w5_nan": ("windowed", (22, 8, 1), 8, dict(W=5, stride=5, pad=0)),
     "win2d_20x12_w7": ("windowed", (20, 12, 8, 2), 8, dict(W=7)),
     "win3d_6x7x8_w3": ("windowed", (6, 7, 8, 8, 1), 8, dict(W=3)),
+    "circ2d_16x6_d8_w5": ("circulant2d", (16, 6, 8, 2), 8, dict(W=5)),       # SURVEY 8f-2 (no reference code: README todo)
 }
 
 
@@ -55,6 +56,9 @@ def main():
         elif kind == "circulant":
             y, l, m = fo.circulant_fa(Q, K, V, kw["W"])
             dq, dk, dvv = fo.circulant_backward(Q, K, V, G, kw["W"])
+        elif kind == "circulant2d":
+            y, l, m = fo.circulant2d_fa(Q, K, V, kw["W"])
+            dq, dk, dvv = fo.circulant2d_backward(Q, K, V, G, kw["W"])
         else:
             y, l, m = fo.windowed_fa(Q, K, V, kw["W"], kw.get("stride"), kw.get("pad"))
             dq, dk, dvv = fo.windowed_backward(Q, K, V, G, kw["W"], kw.get("stride"), kw.get("pad"))
@@ -68,7 +72,11 @@ def main():
     # integer index sets (bit-exact)
     np.savez_compressed(os.path.join(OUT, "index_sets.npz"),
                         circ_16_5=fo.circulant_keys(16, 5), circ_32_8=fo.circulant_keys(32, 8),
-                        win_9x8_w3_s2_p1=fo.window_index((9, 8), 3, 2, 1), win_6x6x6_w5_s5_p2=fo.window_index((6, 6, 6), 5, 5, 2))
+                        win_9x8_w3_s2_p1=fo.window_index((9, 8), 3, 2, 1), win_6x6x6_w5_s5_p2=fo.window_index((6, 6, 6), 5, 5, 2),
+                        circ2d_6x5_w3=fo.circulant2d_keys(6, 5, 3),
+                        # slab plans (plane_lo, plane_hi, win_lo, win_hi, pad_lo) per rank: config-5 volume over 8, config-2 image over 3
+                        slab_64c_w5_s5_p3_g8=np.array([fo.windowed_slab_plan((64, 64, 64), 5, 5, 3, r, 8) for r in range(8)], dtype=np.int64),
+                        slab_64x64_w7_s7_p3_g3=np.array([fo.windowed_slab_plan((64, 64), 7, 7, 3, r, 3) for r in range(3)], dtype=np.int64))
 
 
 if __name__ == "__main__":
