@@ -362,7 +362,7 @@ def test_windowed_tma_gather_variant():
     """Opt-in TMA-gather variant of the windowed forward (FA_WIN_TMA=1; the flag is read once per process, so
     the checker runs in a subprocess): 1-D / 2-D / 3-D exact-cover windows, incl. the config-5 geometry, 2e-3."""
     import os, subprocess, sys
-    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools", "check_win_tma.py")
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "check_win_tma.py")
     r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=600, env=dict(os.environ, FA_WIN_TMA="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 

@@ -1,9 +1,9 @@
 """Prints the max-abs relative error (tests/util.rel_err) of the tcgen05 backward in both bf16 modes
 (default: inputs re-encoded as scaled fp16; FA_FLAG_BF16_INTERNALS: P/dS kept in bf16) against the
-float64 oracle evaluated on the same (Q,K,V,O,dO,l,m).  Usage (GPU box): python tools/bwd_err.py"""
+float64 oracle evaluated on the same (Q,K,V,O,dO,l,m).  Usage (GPU box): python tests/tools/bwd_err.py"""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "flashattention.jl_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import fa_sm100a as fa

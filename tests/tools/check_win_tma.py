@@ -4,7 +4,7 @@ tests/test_gpu_parity.py::test_windowed_tma_gather_variant in a subprocess."""
 import os, sys
 os.environ.setdefault("FA_WIN_TMA", "1")
 import numpy as np, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flashattention.jl_b200"), os.path.join(ROOT, "tests")]
 import fa_sm100a as fa
 from oracle import fa_oracle as fo
