@@ -27,13 +27,6 @@ int cuda_fail(cudaError_t e, const char* what) {
   return FA_ERR_CUDA;
 }
 
-int tc_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
-             int lbo, int sbo, int kstep, int kbox, int afmt, cudaStream_t st);
-int tmem_bw_probe(int mode, int nwarps, int iters, long long* out_dev, cudaStream_t st);
-int umma_rate_probe(int mode, int n_cols, int iters, int blocks, long long* out_dev, cudaStream_t st);
-int tma5d_probe(const void* base, const long long* dims, const long long* strides_bytes, const int* box, const int* coord,
-                unsigned char* out_dev, cudaStream_t st);
-
 namespace {
 
 bool valid_dtype(int dt) { return dt == FA_F32 || dt == FA_F16 || dt == FA_BF16; }
@@ -108,6 +101,11 @@ bool full_cover(const Geo& g) {
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// FA_FLAG_OUT_F32: 16-bit inputs, float32 outputs (the accumulators are stored unrounded).  Only the tcgen05
+// kernels implement it; for Float32 inputs the flag is a no-op.
+bool want_f32_out(int dtype, int flags) { return (flags & FA_FLAG_OUT_F32) && dtype != FA_F32; }
+int no_f32_out() { set_error("FA_FLAG_OUT_F32 needs a shape the tcgen05 kernels cover (16-bit, d == dv in {64,128})"); return FA_ERR_UNSUPPORTED; }
+
 }  // namespace
 }  // namespace fa
 
@@ -168,9 +166,10 @@ int fa_dense_fwd(const void* q, const void* k, const void* v, void* o, float* l,
   if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
   if ((rc = need_device())) return rc;
   const Geo g = dense_geo(N, d, dv, B);
-  FwdArgs a{q, k, v, o, nullptr, l, m};
+  FwdArgs a{q, k, v, o, nullptr, l, m, want_f32_out(dtype, flags) ? 1 : 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(g, dtype)) { set_path("tc"); return tc_fwd(g, a, dtype, st); }
+  if (a.o_f32) return no_f32_out();
   set_path("simt");
   return simt_fwd(g, a, dtype, st);
 }
@@ -195,7 +194,8 @@ int fa_dense_bwd(const void* q, const void* k, const void* v, const void* o, con
   if ((rc = need_device())) return rc;
   const Geo g = dense_geo(N, d, dv, B);
   BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
-  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(g, dtype)) { set_path("tc"); return tc_bwd(g, a, dtype, flags, workspace, static_cast<cudaStream_t>(stream)); }
+  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(g, dtype)) { set_path("tc"); return tc_bwd(g, a, dtype, flags, workspace, static_cast<cudaStream_t>(stream), want_f32_out(dtype, flags) ? 1 : 0); }
+  if (want_f32_out(dtype, flags)) return no_f32_out();
   set_path("simt");
   return simt_bwd(g, a, dtype, static_cast<cudaStream_t>(stream));
 }
@@ -216,9 +216,10 @@ int fa_circulant_fwd(const void* q, const void* k, const void* v, void* o, float
   Geo g;
   if ((rc = circ_geo(g, N, d, dv, B, W))) return rc;
   if ((rc = need_device())) return rc;
-  FwdArgs a{q, k, v, o, nullptr, l, m};
+  FwdArgs a{q, k, v, o, nullptr, l, m, want_f32_out(dtype, flags) ? 1 : 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(g, dtype)) { set_path("tc"); return tc_fwd(g, a, dtype, st); }
+  if (a.o_f32) return no_f32_out();
   set_path("simt");
   return simt_fwd(g, a, dtype, st);
 }
@@ -240,27 +241,28 @@ int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o,
   if (!workspace || workspace_bytes < fa_workspace_bytes_circulant_bwd(N, d, dv, B, W, dtype, flags)) { set_error("workspace too small"); return FA_ERR_WORKSPACE; }
   if ((rc = need_device())) return rc;
   BwdArgs a{q, k, v, o, d_o, l, m, dq, dk, dv_out, nullptr, nullptr, nullptr, static_cast<float*>(workspace)};
-  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(g, dtype)) { set_path("tc"); return tc_bwd(g, a, dtype, flags, workspace, static_cast<cudaStream_t>(stream)); }
+  if (!(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(g, dtype)) { set_path("tc"); return tc_bwd(g, a, dtype, flags, workspace, static_cast<cudaStream_t>(stream), want_f32_out(dtype, flags) ? 1 : 0); }
+  if (want_f32_out(dtype, flags)) return no_f32_out();
   set_path("simt");
   return simt_bwd(g, a, dtype, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------ windowed
-static size_t windowed_fwd_ws(const Geo& g) {
-  return g.overlap ? align256((size_t)g.N * g.dv * g.B * sizeof(float)) : 256;
+// f32out (FA_FLAG_OUT_F32): the fold accumulators are used even without overlap and finalised into float32 outputs
+static size_t windowed_fwd_ws(const Geo& g, bool f32out = false) {
+  return (g.overlap || f32out) ? align256((size_t)g.N * g.dv * g.B * sizeof(float)) : 256;
 }
-static size_t windowed_bwd_ws(const Geo& g) {
+static size_t windowed_bwd_ws(const Geo& g, bool f32out = false) {
   size_t bytes = align256((size_t)g.WD * g.L * g.B * sizeof(float));                 // delta per window slot
-  if (g.overlap) bytes += 2 * align256((size_t)g.N * g.d * g.B * sizeof(float)) + align256((size_t)g.N * g.dv * g.B * sizeof(float));
+  if (g.overlap || f32out) bytes += 2 * align256((size_t)g.N * g.d * g.B * sizeof(float)) + align256((size_t)g.N * g.dv * g.B * sizeof(float));
   return bytes;
 }
 
 size_t fa_workspace_bytes_windowed_fwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
                                        int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
-  (void)dtype; (void)flags;
   Geo g;
   if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
-  return windowed_fwd_ws(g);
+  return windowed_fwd_ws(g, want_f32_out(dtype, flags));
 }
 
 static int windowed_fwd_impl(const Geo& g, const void* q, const void* k, const void* v, void* y, float* l, float* m,
@@ -269,19 +271,21 @@ static int windowed_fwd_impl(const Geo& g, const void* q, const void* k, const v
   int rc;
   if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
   if (!q || !k || !v || !y || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  if (g.overlap && (!workspace || workspace_bytes < windowed_fwd_ws(g))) {
+  const bool f32out = want_f32_out(dtype, flags);
+  if ((g.overlap || f32out) && (!workspace || workspace_bytes < windowed_fwd_ws(g, f32out))) {
     set_error("workspace too small"); return FA_ERR_WORKSPACE;
   }
   if ((rc = need_device())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FwdArgs a{q, k, v, y, nullptr, l, m};
   const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_win_supported(g, dtype);
+  if (f32out && !tc) return no_f32_out();
   set_path(tc ? "tc" : "simt");
-  if (g.overlap) {
+  if (g.overlap || f32out) {
     a.acc = static_cast<float*>(workspace);
     FA_CUDA_TRY(cudaMemsetAsync(a.acc, 0, (size_t)g.N * dv * B * sizeof(float), st));
     if ((rc = tc ? tc_win_fwd(g, a, dtype, st) : simt_fwd(g, a, dtype, st))) return rc;
-    return fold_finalize(g, a.acc, y, (int)dv, dtype, /*divide=*/1, st);     // src/windowed.jl:19
+    return fold_finalize(g, a.acc, y, (int)dv, f32out ? FA_F32 : dtype, /*divide=*/1, st);     // src/windowed.jl:19
   }
   if ((rc = tc ? tc_win_fwd(g, a, dtype, st) : simt_fwd(g, a, dtype, st))) return rc;
   if (!full_cover(g)) return fill_uncovered_nan(g, y, (int)dv, dtype, st);   // 0/0 = NaN
@@ -300,10 +304,9 @@ int fa_windowed_fwd(const void* q, const void* k, const void* v, void* y, float*
 
 size_t fa_workspace_bytes_windowed_bwd(int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
                                        int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
-  (void)dtype; (void)flags;
   Geo g;
   if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
-  return windowed_bwd_ws(g);
+  return windowed_bwd_ws(g, want_f32_out(dtype, flags));
 }
 
 static int windowed_bwd_impl(const Geo& g, const void* q, const void* k, const void* v, const void* d_y,
@@ -313,7 +316,8 @@ static int windowed_bwd_impl(const Geo& g, const void* q, const void* k, const v
   int rc;
   if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
   if (!q || !k || !v || !d_y || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  if (!workspace || workspace_bytes < windowed_bwd_ws(g)) {
+  const bool f32out = want_f32_out(dtype, flags);
+  if (!workspace || workspace_bytes < windowed_bwd_ws(g, f32out)) {
     set_error("workspace too small"); return FA_ERR_WORKSPACE;
   }
   if ((rc = need_device())) return rc;
@@ -323,8 +327,10 @@ static int windowed_bwd_impl(const Geo& g, const void* q, const void* k, const v
   ws += align256((size_t)g.WD * g.L * B * sizeof(float));
   const size_t esz = dtype_size(dtype);
   const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_win_bwd_supported(g, dtype);
+  if (f32out && !tc) return no_f32_out();
   set_path(tc ? "tc" : "simt");
-  if (g.overlap) {
+  if (g.overlap || f32out) {
+    const int odt = f32out ? FA_F32 : dtype;
     const size_t nq = (size_t)g.N * d * B, nv = (size_t)g.N * dv * B;
     a.aq = reinterpret_cast<float*>(ws); ws += align256(nq * 4);
     a.ak = reinterpret_cast<float*>(ws); ws += align256(nq * 4);
@@ -333,9 +339,9 @@ static int windowed_bwd_impl(const Geo& g, const void* q, const void* k, const v
     FA_CUDA_TRY(cudaMemsetAsync(a.ak, 0, nq * 4, st));
     FA_CUDA_TRY(cudaMemsetAsync(a.av, 0, nv * 4, st));
     if ((rc = tc ? tc_win_bwd(g, a, dtype, st) : simt_bwd(g, a, dtype, st))) return rc;
-    if ((rc = fold_finalize(g, a.aq, dq, (int)d, dtype, 0, st))) return rc;   // adjoint of unfold: fold, no division
-    if ((rc = fold_finalize(g, a.ak, dk, (int)d, dtype, 0, st))) return rc;
-    return fold_finalize(g, a.av, dv_out, (int)dv, dtype, 0, st);
+    if ((rc = fold_finalize(g, a.aq, dq, (int)d, odt, 0, st))) return rc;   // adjoint of unfold: fold, no division
+    if ((rc = fold_finalize(g, a.ak, dk, (int)d, odt, 0, st))) return rc;
+    return fold_finalize(g, a.av, dv_out, (int)dv, odt, 0, st);
   }
   if (!full_cover(g)) {   // uncovered positions receive no gradient
     FA_CUDA_TRY(cudaMemsetAsync(dq, 0, (size_t)g.N * d * B * esz, st));
@@ -604,39 +610,6 @@ int fa_release_host_staging(void) {
     }
   }
   return FA_OK;
-}
-
-// ------------------------------------------------------------------------------ diagnostics
-// One UMMA tile with caller-supplied descriptor fields (see fa_tc_probe.cu).  Not a product API.
-int fa_debug_umma_probe(int mode, const void* a, const void* b, const float* p, float* out, int D, int dtype,
-                        int lbo, int sbo, int kstep, int kbox, int afmt, void* stream) {
-  int rc = need_device();
-  if (rc) return rc;
-  return tc_probe(mode, a, b, p, out, D, dtype, lbo, sbo, kstep, kbox, afmt, static_cast<cudaStream_t>(stream));
-}
-
-// TMEM read/write bandwidth microbenchmark (see fa_tc_probe.cu).  Not a product API.
-int fa_debug_tmem_bw(int mode, int nwarps, int iters, long long* out_dev, void* stream) {
-  int rc = need_device();
-  if (rc) return rc;
-  if ((nwarps != 1 && nwarps != 4 && nwarps != 8) || iters <= 0 || !out_dev) { set_error("bad probe arguments"); return FA_ERR_INVALID; }
-  return tmem_bw_probe(mode, nwarps, iters, out_dev, static_cast<cudaStream_t>(stream));
-}
-
-// tcgen05.mma throughput by operand source and N (see fa_tc_probe.cu).  Not a product API.
-int fa_debug_umma_rate(int mode, int n_cols, int iters, int blocks, long long* out_dev, void* stream) {
-  int rc = need_device();
-  if (rc) return rc;
-  if (mode < 0 || mode > 7 || n_cols < 16 || n_cols > 256 || n_cols % 16 || iters <= 0 || blocks <= 0 || !out_dev) { set_error("bad probe arguments"); return FA_ERR_INVALID; }
-  return umma_rate_probe(mode, n_cols, iters, blocks, out_dev, static_cast<cudaStream_t>(stream));
-}
-
-// One 5-D TMA box load (bf16 elements) copied back out (see fa_tc_probe.cu).  Not a product API.
-int fa_debug_tma5d(const void* base, const long long* dims, const long long* strides_bytes, const int* box, const int* coord,
-                   unsigned char* out_dev, void* stream) {
-  int rc = need_device();
-  if (rc) return rc;
-  return tma5d_probe(base, dims, strides_bytes, box, coord, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -6,6 +6,15 @@
 namespace fa {
 namespace {
 
+// (mx, sum) <- merge with a partial (om, os).  -inf entries (masked scores) contribute 0 and never produce
+// exp(-inf - -inf) = NaN: the reference's fused_softmax! (src/fused_softmax.jl:20-24) gives 0 for them.
+__device__ __forceinline__ void online_merge(float& mx, float& sum, float om, float os) {
+  const float mn = fmaxf(mx, om);
+  const float a = (mx == -INFINITY) ? 0.f : expf(mx - mn), b = (om == -INFINITY) ? 0.f : expf(om - mn);
+  sum = sum * a + os * b;
+  mx = mn;
+}
+
 // dim 1: one warp per (column n, batch b); lanes stride the contiguous M axis.
 template <typename T>
 __global__ void softmax_dim1_kernel(T* __restrict__ out, const T* __restrict__ in, long long M, long long cols) {
@@ -16,19 +25,10 @@ __global__ void softmax_dim1_kernel(T* __restrict__ out, const T* __restrict__ i
     T* y = out + col * M;
     float mx = -INFINITY, sum = 0.f;
     for (long long i = lane; i < M; i += 32) {            // online max / sum
-      const float v = to_f32<T>(x[i]);
-      const float mn = fmaxf(mx, v);
-      sum = sum * expf(mx - mn) + expf(v - mn);
-      mx = mn;
+      online_merge(mx, sum, to_f32<T>(x[i]), 1.f);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mn = fmaxf(mx, om);
-      const float a = (mx == -INFINITY) ? 0.f : expf(mx - mn), b = (om == -INFINITY) ? 0.f : expf(om - mn);
-      sum = sum * a + os * b;
-      mx = mn;
-    }
+    for (int o = 16; o > 0; o >>= 1) online_merge(mx, sum, __shfl_xor_sync(0xffffffffu, mx, o), __shfl_xor_sync(0xffffffffu, sum, o));
     const float inv = 1.f / sum;
     for (long long i = lane; i < M; i += 32) y[i] = from_f32<T>(expf(to_f32<T>(x[i]) - mx) * inv);
   }
@@ -44,21 +44,11 @@ __global__ void softmax_dim2_kernel(T* __restrict__ out, const T* __restrict__ i
     T* y = out + b * M * N + i;
     float mx = -INFINITY, sum = 0.f;
     for (long long n = 0; n < N; ++n) {
-      const float v = to_f32<T>(x[n * M]);
-      const float mn = fmaxf(mx, v);
-      sum = sum * expf(mx - mn) + expf(v - mn);
-      mx = mn;
+      online_merge(mx, sum, to_f32<T>(x[n * M]), 1.f);
     }
     const float inv = 1.f / sum;
     for (long long n = 0; n < N; ++n) y[n * M] = from_f32<T>(expf(to_f32<T>(x[n * M]) - mx) * inv);
   }
-}
-
-__device__ __forceinline__ void online_merge(float& mx, float& sum, float om, float os) {
-  const float mn = fmaxf(mx, om);
-  const float a = (mx == -INFINITY) ? 0.f : expf(mx - mn), b = (om == -INFINITY) ? 0.f : expf(om - mn);
-  sum = sum * a + os * b;
-  mx = mn;
 }
 
 // dim 1, few long columns (the vector case of bench/softmax.jl:8-35): one 1024-thread block per column.

@@ -29,7 +29,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 __all__ = [
-    "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
+    "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "FA_FLAG_OUT_F32", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
     "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys", "circulant2d_keys", "circulant", "batch_circulant",
@@ -42,6 +42,7 @@ _LIB_PATH = os.environ.get("FA_SM100A_LIB", os.path.join(os.path.dirname(_HERE),
 FA_F32, FA_F16, FA_BF16 = 0, 1, 2
 FA_FLAG_FORCE_SIMT = 1
 FA_FLAG_BF16_INTERNALS = 2
+FA_FLAG_OUT_F32 = 4          # 16-bit inputs, float32 outputs (fp32 accumulators stored unrounded; tcgen05 kernels only)
 _DTYPES = {torch.float32: FA_F32, torch.float16: FA_F16, torch.bfloat16: FA_BF16}
 
 
@@ -97,7 +98,6 @@ def _load():
         "fa_ring_dense_fwd": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, vp, ci, ci, vp, sz, vp]),
         "fa_workspace_bytes_ring_dense_bwd": (sz, [i64, i64, i64, i64, ci, ci]),
         "fa_ring_dense_bwd": (ci, [vp] * 10 + [i64, i64, i64, i64, ci, ci, vp, ci, ci, vp, sz, vp]),
-        "fa_debug_umma_probe": (ci, [ci, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)          # AttributeError here == header/library mismatch
@@ -207,6 +207,25 @@ def _workspace(nbytes: int, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def _out_dtype(x: torch.Tensor, flags: int):
+    return torch.float32 if (flags & FA_FLAG_OUT_F32) else x.dtype
+
+
+def _check_out(name: str, t: torch.Tensor, shape, dtype, like: torch.Tensor):
+    """The in-place entry points write through raw pointers: a caller-allocated output of the wrong eltype, shape,
+    layout or device would be a silent out-of-bounds write (the Julia signatures are typed; mirror that)."""
+    if not isinstance(t, torch.Tensor):
+        raise FaError(f"{name} must be a tensor")
+    if t.dtype != dtype:
+        raise FaError(f"{name} must have eltype {dtype} (got {t.dtype}); l and m are always float32 (include/fa_sm100a.h)")
+    if tuple(int(s) for s in t.shape) != tuple(int(s) for s in shape):
+        raise FaError(f"{name} must have shape {tuple(shape)} (got {tuple(t.shape)})")
+    if t.device != like.device:
+        raise FaError(f"{name} must live on {like.device} (got {t.device})")
+    if not is_jl_contiguous(t):
+        raise FaError(f"{name} must be dense column-major (see jl_empty)")
+
+
 def _cur_dev() -> int:
     # host entry points: the library itself reports FA_ERR_CUDA when there is no device
     return torch.cuda.current_device() if torch.cuda.is_available() else 0
@@ -223,6 +242,9 @@ def dense_fa_(O, l, m, Q, K, V, flags: int = 0):
     if tuple(K.shape) != tuple(Q.shape) or V.shape[0] != Q.shape[0] or V.shape[-1] != Q.shape[-1]:
         raise FaError("dense_fa!: Q, K must have equal shapes and V the same N and batch (src/dense.jl:29,72)")
     Q, K, V = (jl_array(t) for t in (Q, K, V))
+    _check_out("O", O, (N, dv, B), _out_dtype(Q, flags), Q)
+    _check_out("l", l, (N, 1, B), torch.float32, Q)
+    _check_out("m", m, (N, 1, B), torch.float32, Q)
     if Q.is_cuda:
         with torch.cuda.device(Q.device):
             _check(lib.fa_dense_fwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(l), _ptr(m),
@@ -243,7 +265,7 @@ def dense_fa(q, k, v, flags: int = 0):
     Q = q if q.ndim == 3 else _jl_reshape(q, (N, d, B))
     K = k if k.ndim == 3 else _jl_reshape(k, (N, d, B))
     V = v if v.ndim == 3 else _jl_reshape(v, (N, dv, B))
-    O = jl_empty((N, dv, B), q.dtype, q.device)
+    O = jl_empty((N, dv, B), _out_dtype(q, flags), q.device)
     l = jl_empty((N, 1, B), torch.float32, q.device)
     m = jl_empty((N, 1, B), torch.float32, q.device)
     dense_fa_(O, l, m, Q, K, V, flags)
@@ -267,7 +289,7 @@ def dense_fa_backward(Q, K, V, O, dO, l, m, flags: int = 0):
     N, d, B = _flatten3(Q)
     dv = int(V.shape[-2])
     l, m = (jl_array(t, torch.float32) for t in (l, m))
-    dQ, dK, dV = (jl_empty(t.shape, t.dtype, t.device) for t in (Q, K, V))
+    dQ, dK, dV = (jl_empty(t.shape, _out_dtype(t, flags), t.device) for t in (Q, K, V))
     ws = _workspace(lib.fa_workspace_bytes_dense_bwd(N, d, dv, B, _dt(Q), flags), Q.device)
     with torch.cuda.device(Q.device):
         _check(lib.fa_dense_bwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m),
@@ -396,7 +418,7 @@ def windowed_fa(q, k, v, windowsize: int, stride: Optional[int] = None, pad: Opt
     for n in nw:
         L *= n
     WD = W ** len(spatial)
-    y = jl_empty(spatial + (dv, B), q.dtype, q.device)
+    y = jl_empty(spatial + (dv, B), _out_dtype(q, flags), q.device)
     l = jl_empty((WD, 1, L, B), torch.float32, q.device)
     m = jl_empty((WD, 1, L, B), torch.float32, q.device)
     if q.is_cuda:
@@ -428,7 +450,7 @@ def windowed_fa_backward(q, k, v, dy, l, m, windowsize: int, stride=None, pad=No
     spatial = tuple(int(s) for s in q.shape[:-2])
     d, dv, B = int(q.shape[-2]), int(v.shape[-2]), int(q.shape[-1])
     dims = _i64arr(spatial)
-    dq, dk, dvv = (jl_empty(t.shape, t.dtype, t.device) for t in (q, k, v))
+    dq, dk, dvv = (jl_empty(t.shape, _out_dtype(t, flags), t.device) for t in (q, k, v))
     ws = _workspace(lib.fa_workspace_bytes_windowed_bwd(len(spatial), dims, d, dv, B, W, stride, pad, _dt(q), flags), q.device)
     with torch.cuda.device(q.device):
         _check(lib.fa_windowed_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(dy), _ptr(l), _ptr(m), _ptr(dq), _ptr(dk), _ptr(dvv),
@@ -574,6 +596,9 @@ def circulant_fa_(O, l, m, Q, K, V, W: int, flags: int = 0):
     Q, K, V = (jl_array(t) for t in (Q, K, V))
     if Q.ndim == 4:                       # 2-D periodic neighbourhood (the reference's todo, README.md:38-41,53)
         X, Y, d, B = (int(s) for s in Q.shape)
+        _check_out("O", O, (X, Y, int(V.shape[2]), B), Q.dtype, Q)
+        _check_out("l", l, (X * Y, 1, B), torch.float32, Q)
+        _check_out("m", m, (X * Y, 1, B), torch.float32, Q)
         with torch.cuda.device(Q.device):
             _check(lib.fa_circulant2d_fwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(l), _ptr(m), X, Y, d, int(V.shape[2]), B, int(W),
                                           _dt(Q), flags, _stream(Q)), "fa_circulant2d_fwd")
@@ -582,6 +607,9 @@ def circulant_fa_(O, l, m, Q, K, V, W: int, flags: int = 0):
         raise FaError("circulant_fa!: Q, K, V must be (N, d, B) or (X, Y, d, B)")
     N, d, B = (int(s) for s in Q.shape)
     dv = int(V.shape[1])
+    _check_out("O", O, (N, dv, B), _out_dtype(Q, flags), Q)
+    _check_out("l", l, (N, 1, B), torch.float32, Q)
+    _check_out("m", m, (N, 1, B), torch.float32, Q)
     if Q.is_cuda:
         with torch.cuda.device(Q.device):
             _check(lib.fa_circulant_fwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(l), _ptr(m), N, d, dv, B, int(W),
@@ -602,7 +630,7 @@ def circulant_fa(Q, K, V, W: int, flags: int = 0):
         m = jl_empty((X * Y, 1, B), torch.float32, Q.device)
         return circulant_fa_(O, l, m, Q, K, V, W, flags)
     N, d, B = (int(s) for s in Q.shape)
-    O = jl_empty((N, int(V.shape[1]), B), Q.dtype, Q.device)
+    O = jl_empty((N, int(V.shape[1]), B), _out_dtype(Q, flags), Q.device)
     l = jl_empty((N, 1, B), torch.float32, Q.device)
     m = jl_empty((N, 1, B), torch.float32, Q.device)
     return circulant_fa_(O, l, m, Q, K, V, W, flags)
@@ -624,7 +652,7 @@ def circulant_fa_backward(Q, K, V, O, dO, l, m, W: int, flags: int = 0):
         return dQ, dK, dV
     N, d, B = (int(s) for s in Q.shape)
     dv = int(V.shape[1])
-    dQ, dK, dV = (jl_empty(t.shape, t.dtype, t.device) for t in (Q, K, V))
+    dQ, dK, dV = (jl_empty(t.shape, _out_dtype(t, flags), t.device) for t in (Q, K, V))
     ws = _workspace(lib.fa_workspace_bytes_circulant_bwd(N, d, dv, B, int(W), _dt(Q), flags), Q.device)
     with torch.cuda.device(Q.device):
         _check(lib.fa_circulant_bwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m),

@@ -57,6 +57,12 @@ typedef enum fa_dtype {
                                     q,k,v,dO and 4*N*d*B*2 bytes of workspace; gradients then carry the 2^-9 rounding
                                     of bf16 P/dS (max-abs error 2-3e-3 of max instead of < 2e-3). */
 
+#define FA_FLAG_OUT_F32 4        /* 16-bit inputs on the tcgen05 kernels: outputs (o / y, dq, dk, dv) are float32 buffers and
+                                    receive the fp32 accumulators unrounded.  Separates the COMPUTE error (north_star:
+                                    2e-3) from the 2^-8 / 2^-11 rounding of a bf16 / fp16 result; FA_ERR_UNSUPPORTED when
+                                    the shape falls to the exact-fp32 kernels, no-op for Float32 inputs.  Windowed calls
+                                    then need the workspace fa_workspace_bytes_windowed_* report for these flags. */
+
 /* ---- host helpers -------------------------------------------------------------------- */
 int fa_version(void);                       /* FA_VERSION_MAJOR*100 + FA_VERSION_MINOR     */
 const char* fa_last_error_string(void);     /* thread-local, never NULL                    */

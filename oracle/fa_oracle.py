@@ -38,7 +38,7 @@ __all__ = [
     "dense_fa_backward_blocked", "window_counts", "window_index", "window", "unwindow",
     "windowed_dpa", "windowed_fa", "block_fa", "block_dpa", "windowed_backward",
     "circshift_index", "cartesian_circulant", "circulant_keys", "circulant_dpa",
-    "circulant_fa", "circulant_backward", "fused_softmax",
+    "circulant_fa", "circulant_backward", "circulant_backward_given", "circulant2d_backward_given", "fused_softmax",
 ]
 
 
@@ -609,6 +609,29 @@ def circulant_backward_given(Q, K, V, O, dO, l, m, W: int):
     np.add.at(dK, flat, (dS[:, :, None, :] * Q[None, :, :, :]).reshape(-1, d, B) * tau)
     np.add.at(dV, flat, (P[:, :, None, :] * dO[None, :, :, :]).reshape(-1, V.shape[1], B))
     return _F(dQ), _F(dK), _F(dV)
+
+
+def circulant2d_backward_given(Q, K, V, O, dO, l, m, W: int):
+    """2-D periodic neighbourhood form of :func:`circulant_backward_given`: the flash backward
+    (src_cpp/FlashAttention.cpp:238-246) restricted to the W x W neighbourhood, on the SAVED (O, l, m)."""
+    Q, K, V, O, dO = _F(Q), _F(K), _F(V), _F(O), _F(dO)
+    X, Y, d, B = Q.shape
+    dv = V.shape[2]
+    q, k, v, o, g = (t.reshape(X * Y, t.shape[2], B, order="F") for t in (Q, K, V, O, dO))
+    keys = circulant2d_keys(X, Y, W)
+    tau = Q.dtype.type(1) / Q.dtype.type(math.sqrt(d))
+    S = np.einsum("ikb,wikb->wib", q, k[keys]) * tau
+    P = np.exp(S - np.asarray(m).reshape(1, X * Y, B)) / np.asarray(l).reshape(1, X * Y, B)
+    dP = np.einsum("icb,wicb->wib", g, v[keys])
+    dS = P * (dP - (g * o).sum(axis=1)[None, :, :])
+    dq = np.einsum("wib,wikb->ikb", dS, k[keys]) * tau
+    dk = np.zeros_like(k)
+    dvv = np.zeros_like(v)
+    flat = keys.reshape(-1)
+    np.add.at(dk, flat, (dS[:, :, None, :] * q[None, :, :, :]).reshape(-1, d, B) * tau)
+    np.add.at(dvv, flat, (P[:, :, None, :] * g[None, :, :, :]).reshape(-1, dv, B))
+    rs = lambda t, c: _F(t.reshape(X, Y, c, B, order="F"))
+    return rs(dq, d), rs(dk, d), rs(dvv, dv)
 
 
 # --------------------------------------------------------------------------------------

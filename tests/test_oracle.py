@@ -322,3 +322,12 @@ def test_circulant2d_oracle_definition():
             args_p[which][idx] += eps
             args_m[which][idx] -= eps
             assert abs((f(*args_p) - f(*args_m)) / (2 * eps) - gr[idx]) < 1e-7
+
+
+def test_circulant2d_backward_given_equals_recomputing_form():
+    """the (O, l, m)-taking form of the 2-D circulant backward equals the recomputing one when handed exact stats"""
+    rng = np.random.default_rng(5)
+    Q, K, V, G = (np.asfortranarray(rng.standard_normal((8, 6, 4, 2))) for _ in range(4))
+    O, l, m = fo.circulant2d_fa(Q, K, V, 3)
+    for a, b in zip(fo.circulant2d_backward_given(Q, K, V, O, G, l, m, 3), fo.circulant2d_backward(Q, K, V, G, 3)):
+        assert np.abs(a - b).max() < 1e-12

@@ -27,10 +27,12 @@ def to_np(t):
     return np.asfortranarray(t.detach().float().cpu().numpy().astype(np.float64))
 
 
-# round-to-nearest half-ulp (relative) of the 16-bit STORAGE types: bf16 keeps 8 significand bits,
-# fp16 11.  A result stored in bf16 can be off by 2^-8 = 3.9e-3 of its own magnitude no matter how
-# it was computed, which is larger than the 2e-3 compute tolerance; the two are kept apart.
-STORAGE_HALF_ULP = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}
+# round-to-nearest half-ulp (relative) of bf16 STORAGE: bf16 keeps 8 significand bits, so a result stored in bf16
+# can be off by 2^-8 = 3.9e-3 of its own magnitude no matter how it was computed -- more than the 2e-3 compute
+# tolerance.  The two are kept apart here, and the compute error alone is PROVEN under 2e-3 with no allowance by the
+# FA_FLAG_OUT_F32 legs (tests/test_gpu_parity_r2.py: same kernels, fp32 accumulators stored unrounded).
+# fp16 storage (2^-11 = 4.9e-4) gets NO allowance: fp16 results must meet 2e-3 as stored.
+STORAGE_HALF_ULP = {torch.bfloat16: 2.0 ** -8}
 
 
 def rel_err(got, want, storage=None, want_rounded=False):

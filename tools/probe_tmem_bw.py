@@ -5,7 +5,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "flashattention.jl_b200"))
 import fa_sm100a as fa
-f = fa.lib.fa_debug_tmem_bw
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from _probe_lib import probe_lib
+f = probe_lib().fa_debug_tmem_bw
 f.restype = ctypes.c_int
 f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(8, dtype=torch.int64, device="cuda")

@@ -13,6 +13,8 @@ import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "flashattention.jl_b200"))
 import fa_sm100a as fa  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _probe_lib import probe_lib  # noqa: E402
 
 
 def run(mode, D, dtype, lbo, sbo, kstep, kbox, afmt=-1):
@@ -29,11 +31,11 @@ def run(mode, D, dtype, lbo, sbo, kstep, kbox, afmt=-1):
         p = torch.rand(128, 128, device="cuda").to(pdt).float().contiguous()
         out = torch.zeros(128, D, device="cuda")
         want = p.double() @ b.double().T                           # O[i][c] = sum_j P[i][j] V[c][j]
-    rc = fa.lib.fa_debug_umma_probe(mode, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+    rc = probe_lib().fa_debug_umma_probe(mode, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
                                     None if p is None else ctypes.c_void_p(p.data_ptr()),
                                     ctypes.c_void_p(out.data_ptr()), D, code, lbo, sbo, kstep, kbox, afmt, None)
     if rc != 0:
-        return f"rc={rc} {fa.lib.fa_last_error_string().decode()}"
+        return f"rc={rc} {probe_lib().fa_last_error_string().decode()}"
     torch.cuda.synchronize()
     err = (out.double() - want).abs().max().item() / want.abs().max().item()
     return err

@@ -6,7 +6,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "flashattention.jl_b200"))
 import fa_sm100a as fa
-f = fa.lib.fa_debug_umma_rate
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from _probe_lib import probe_lib
+f = probe_lib().fa_debug_umma_rate
 f.restype = ctypes.c_int
 f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
@@ -17,7 +19,7 @@ for blocks in (1,):
         for n in (64, 128, 256):
             for _ in range(2):
                 rc = f(mode, n, iters, blocks, out.data_ptr(), None)
-                assert rc == 0, fa.lib.fa_last_error_string()
+                assert rc == 0, probe_lib().fa_last_error_string()
                 torch.cuda.synchronize()
             clk = int(out[:blocks].max()) / (iters * 8)
             ideal = 128 * n * 16 * 2 / 8192
