@@ -12,6 +12,13 @@ trailing batch dim with no collective, so N GPUs = N independent sha
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launch stream, barrier +
 synchronize on both sides, max over ranks; inputs (3 GiB) exceed L2 (126 MB).
+
+Besides `value` the line carries: `e2e` (the same config through fa_dense_fwd_host on page-locked HOST buffers, H2D +
+kernel + D2H inside the timed region, B = 512 per GPU), `roofline`, `cpu_baseline`, and `extra` = the other legs of the
+named configs (dense backward, C4 circulant, C5 / C2 windowed) plus -- for N > 1 -- the two legs that put real bytes
+on NVLink / split one problem over the GPUs: `ring_dense` (ONE N*16384-token sequence sharded by tokens,
+K/V blocks round the ring by ncclSend/ncclRecv, forward + backward, with a parity check against the single-GPU
+kernel on rank 0) and `slab_windowed` (ONE 256^3 volume cut into slabs on window boundaries).
 """
 import argparse
 import json
@@ -173,6 +180,7 @@ def main():
     for _ in range(warmup):
         step()
     assert fa.last_path() == "tc", "headline config must run on the tcgen05 path"
+    kernel_name = "tc_fwd_kernel<128,bf16> (csrc/fa_tc_fwd.cu)"
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -232,8 +240,7 @@ def main():
         Bc = 512 // world
         cq, ck, cv = (fa.jl_empty((16384, 64, Bc), bf, dev).normal_() for _ in range(3))
         cO = fa.jl_empty((16384, 64, Bc), bf, dev); cl = fa.jl_empty((16384, 1, Bc), torch.float32, dev); cm = fa.jl_empty((16384, 1, Bc), torch.float32, dev)
-        # best of two passes: the leg follows the full-batch dense backward, and the first pass can still see its clocks
-        tc_ = min(timeit(lambda: fa.circulant_fa_(cO, cl, cm, cq, ck, cv, 255), args.steps) for _ in range(2))
+        tc_ = timeit(lambda: fa.circulant_fa_(cO, cl, cm, cq, ck, cv, 255), max(args.steps, 10))
         by = (4 * 16384 * 64 * 2 + 8 * 16384) * Bc
         extra["C4_circulant_fwd"] = {"ms": tc_, "batch_per_gpu": Bc, "tflops_per_gpu": 4.0 * 16384 * 255 * 64 * Bc / tc_ / 1e9,
                                      "alg_gbs_per_gpu": by / tc_ / 1e6, "frac_hbm_peak": by / tc_ / 1e6 / peaks_x["hbm_gbs"],
@@ -286,46 +293,154 @@ def main():
         del iq, ik, iv, ig, iy, il, im
         torch.cuda.empty_cache()
 
-    # ---- end to end: host (pinned) buffers through the public API, H2D + kernel + D2H every step
+        # ---- N > 1 only: the two legs with a real multi-GPU data plane
+        if world > 1:
+            # (1) ring attention: ONE sequence of world*16384 tokens, d = 128, 8 heads, bf16, sharded by tokens; K/V blocks
+            #     travel round the ring over NVLink (ncclSend/ncclRecv inside fa_ring_dense_fwd/_bwd), overlapped with the
+            #     tcgen05 kernels.  Per-GPU rate, fraction of the same kernel on ONE block without any exchange, and parity
+            #     of rank 0's slice against the single-GPU kernel on the whole (gathered) sequence.
+            Nl, Hh = 16384, 8
+            rq, rk, rv, rg = (fa.jl_empty((Nl, D, Hh), bf, dev).normal_() for _ in range(4))
+            rO, rl, rm = fa.ring_dense_fa(rq, rk, rv)
+            t_rf = timeit(lambda: fa.ring_dense_fa(rq, rk, rv), 5)
+            t_rb = timeit(lambda: fa.ring_dense_fa_backward(rq, rk, rv, rO, rg, rl, rm), 3)
+            bO, bl, bm = (fa.jl_empty(sh, dt, dev) for sh, dt in (((Nl, D, Hh), bf), ((Nl, 1, Hh), torch.float32), ((Nl, 1, Hh), torch.float32)))
+            t_blk = timeit(lambda: fa.dense_fa_(bO, bl, bm, rq, rk, rv), 10)        # one block, no exchange
+            ntot = Nl * world
+            ff, fb = 4.0 * Nl * ntot * D * Hh, 10.0 * Nl * ntot * D * Hh              # per rank
+            gath = [torch.empty(Hh, D, Nl, dtype=bf, device=dev) for _ in range(world)]
+            full = []
+            for t_ in (rq, rk, rv):                                                   # gather the shards (check only, untimed)
+                dist.all_gather(gath, t_.permute(2, 1, 0).contiguous())
+                full.append(fa.jl_array(torch.cat(gath, dim=2).permute(2, 1, 0)))
+            ring_err = None
+            if rank == 0:
+                fO, fl, fm = fa.dense_fa(*full, flags=fa.FA_FLAG_OUT_F32)
+                ref = fO[:Nl].float()
+                ring_err = float((rO.float() - ref).abs().max() / ref.abs().max())
+                lse_err = float(((rl.log() + rm) - (fl[:Nl].log() + fm[:Nl])).abs().max())
+                del fO, fl, fm
+            del full, gath
+            kv_bytes = 2 * Nl * D * Hh * 2 * (world - 1)
+            extra["ring_dense"] = {
+                "sequence_tokens": ntot, "tokens_per_gpu": Nl, "d": D, "heads": Hh, "dtype": "bf16",
+                "fwd_ms": t_rf, "bwd_ms": t_rb, "fwd_tflops_per_gpu": ff / t_rf / 1e9, "bwd_tflops_per_gpu": fb / t_rb / 1e9,
+                "single_block_kernel_ms": t_blk, "fwd_frac_of_single_gpu_kernel": (t_blk * world) / t_rf,
+                "nvlink_bytes_sent_per_gpu_fwd": kv_bytes, "nvlink_ms_if_exposed_at_770GBs": kv_bytes / 770e6,
+                "ring_parity_err": ring_err, "ring_parity_lse_abs_err": lse_err if rank == 0 else None,
+                "parity": "rank 0 slice vs single-GPU dense_fa (fp32 output) on the gathered sequence, max-abs / max-abs"}
+            del rq, rk, rv, rg, rO, rl, rm, bO, bl, bm
+            torch.cuda.empty_cache()
+            # (2) ONE 256^3 windowed volume (W = 5, stride 5, pad 3, d = 64, bf16) cut into slabs on window boundaries
+            #     (no exchange needed: non-overlapping windows); rank 0 also runs the whole volume for the speed-up and a
+            #     bit-for-bit check of its slab.
+            S3 = 256
+            plan = fa.windowed_slab_plan((S3, S3, S3), 5, 5, 3, rank, world)
+            planes = plan.plane_hi - plan.plane_lo
+            sq, sk, sv, sg = (fa.jl_empty((S3, S3, planes, 64, 1), bf, dev).normal_() for _ in range(4))
+            sy, sl_, sm_ = fa.windowed_fa_slab(sq, sk, sv, 5, plan, stride=5, pad=3)
+            t_sf = timeit(lambda: fa.windowed_fa_slab(sq, sk, sv, 5, plan, stride=5, pad=3), 5)
+            t_sb = timeit(lambda: fa.windowed_fa_slab_backward(sq, sk, sv, sg, sl_, sm_, 5, plan, stride=5, pad=3), 3)
+            cover = torch.tensor([planes, plan.nwin], device=dev, dtype=torch.int64)
+            dist.all_reduce(cover)
+            one = None
+            gq = [torch.empty(0, device=dev)]
+            shapes = [None] * world
+            dist.all_gather_object(shapes, planes)
+            parts = {}
+            for name, t_ in (("q", sq), ("k", sk), ("v", sv)):                        # gather the slabs on every rank (check only)
+                bufs = [torch.empty(1, 64, shapes[r], S3, S3, dtype=bf, device=dev) for r in range(world)]
+                dist.all_gather(bufs, t_.permute(4, 3, 2, 1, 0).contiguous())
+                parts[name] = fa.jl_array(torch.cat(bufs, dim=2).permute(4, 3, 2, 1, 0)) if rank == 0 else None
+                del bufs
+            if rank == 0:
+                fy, fl_, fm_ = fa.windowed_fa(parts["q"], parts["k"], parts["v"], 5, 5, 3)
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); a_.record()
+                for _ in range(3):
+                    fa.windowed_fa(parts["q"], parts["k"], parts["v"], 5, 5, 3)
+                b_.record(); torch.cuda.synchronize()
+                one = a_.elapsed_time(b_) / 3
+                same = bool(torch.equal(fy[:, :, plan.plane_lo:plan.plane_hi].contiguous(), sy.contiguous()))
+                del fy, fl_, fm_
+            dist.barrier()
+            ntok3 = S3 ** 3
+            extra["slab_windowed"] = {
+                "volume": [S3, S3, S3], "W": 5, "stride": 5, "pad": 3, "d": 64, "dtype": "bf16",
+                "planes_covered": int(cover[0]), "window_planes_covered": int(cover[1]),
+                "fwd_ms": t_sf, "bwd_ms": t_sb, "one_gpu_fwd_ms": one, "fwd_speedup_vs_one_gpu": (one / t_sf) if one else None,
+                "fwd_alg_gbs_total": 4 * ntok3 * 64 * 2 / t_sf / 1e6, "bwd_alg_gbs_total": 7 * ntok3 * 64 * 2 / t_sb / 1e6,
+                "slab_bitwise_equal_to_one_gpu": same if rank == 0 else None}
+            del sq, sk, sv, sg, sy, sl_, sm_, parts
+            torch.cuda.empty_cache()
+
+    # ---- end to end: HOST buffers through the public API (fa_dense_fwd_host), H2D + kernel + D2H every step, on the
+    #      named config (B = 512 per GPU: 3 GiB in, 1 GiB + stats out).  The buffers are page-locked and NUMA-local to the
+    #      rank's GPU (fa_host_alloc) -- with 8 ranks streaming at once the shared host side is the limiter, so the line
+    #      also reports the host<->device copy rates measured the same way (all ranks at once) as the ceiling.
     e2e = None
     if not args.no_e2e:
-        Be = min(Bn, 128)                              # bounded pinned host memory (1 GiB of tensors)
-        hq, hk, hv = (fa.jl_empty((N, D, Be), bf, "cpu") for _ in range(3))
+        Be = Bn
+        hq, hk, hv = (fa.jl_host_empty((N, D, Be), bf, local) for _ in range(3))
         for t_h, t_d in ((hq, q), (hk, k), (hv, v)):
-            t_h.permute(2, 1, 0).copy_(t_d.permute(2, 1, 0)[:Be])
-        hq, hk, hv = (fa.jl_array(t.permute(2, 1, 0).contiguous().pin_memory().permute(2, 1, 0)) for t in (hq, hk, hv))
-        hO = fa.jl_array(torch.empty(Be, D, N, dtype=bf).pin_memory().permute(2, 1, 0))
-        hl = fa.jl_array(torch.empty(Be, 1, N, dtype=torch.float32).pin_memory().permute(2, 1, 0))
-        hm = fa.jl_array(torch.empty(Be, 1, N, dtype=torch.float32).pin_memory().permute(2, 1, 0))
-        fa.dense_fa_(hO, hl, hm, hq, hk, hv)           # warm-up (allocations, first touch)
+            t_h.permute(2, 1, 0).copy_(t_d.permute(2, 1, 0))
+        hO = fa.jl_host_empty((N, D, Be), bf, local)
+        hl = fa.jl_host_empty((N, 1, Be), torch.float32, local)
+        hm = fa.jl_host_empty((N, 1, Be), torch.float32, local)
+        fa.dense_fa_(hO, hl, hm, hq, hk, hv)           # warm-up (staging arena, first touch)
         barrier()
+        ne = max(3, min(args.steps, 5))
         t0 = time.perf_counter()
-        ne = 3
         for _ in range(ne):
             fa.dense_fa_(hO, hl, hm, hq, hk, hv)       # synchronises before returning
         barrier()
         te = (time.perf_counter() - t0) / ne
+        # ceiling: plain pinned copies of the same bytes, every rank at once (H2D and D2H overlapped on two streams)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            for t_h, t_d in ((hq, q), (hk, k), (hv, v)):
+                t_d.permute(2, 1, 0).copy_(t_h.permute(2, 1, 0), non_blocking=True)
+        with torch.cuda.stream(s2):
+            hO.permute(2, 1, 0).copy_(O.permute(2, 1, 0), non_blocking=True)
+        barrier()
+        tcopy = time.perf_counter() - t0
         if world > 1:
-            tm = torch.tensor([te], device=dev)
+            tm = torch.tensor([te, tcopy], device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            te = float(tm.item())
+            te, tcopy = float(tm[0].item()), float(tm[1].item())
+        h2d, d2h = 3 * N * D * Be * 2, N * D * Be * 2 + 2 * N * Be * 4
         e2e = {"value": FLOPS_PER_BATCH_ELT * Be * world / te / 1e12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": 3 * N * D * Be * 2, "d2h_bytes_per_step": N * D * Be * 2 + 2 * N * Be * 4,
-               "batch_per_gpu": Be, "ms_per_step": te * 1e3,
-               "api": "fa_dense_fwd_host via fa_sm100a.dense_fa_ on pinned CPU tensors"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "batch_per_gpu": Be, "ms_per_step": te * 1e3, "steps": ne,
+               "h2d_gbs_aggregate": h2d * world / te / 1e9, "d2h_gbs_aggregate": d2h * world / te / 1e9,
+               "copy_only_ms": tcopy * 1e3, "copy_only_h2d_gbs_aggregate": h2d * world / tcopy / 1e9,
+               "frac_of_copy_ceiling": tcopy / te,
+               "host_memory": "page-locked, NUMA-local to each rank's GPU (fa_host_alloc)",
+               "api": "fa_dense_fwd_host via fa_sm100a.dense_fa_ on host tensors (3-stream chunked pipeline)"}
+        del hq, hk, hv, hO, hl, hm
 
     if rank == 0:
         peaks = measured_peaks()
+        traffic, traffic_src = None, "no ncu capture of this kernel at this batch in profiles/traffic.json"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(f"dense_fwd_d{D}_bf16_N{N}_B{Bn}")
+            if ent:
+                traffic, traffic_src = ent["dram_bytes"], f"bytes per launch, ncu --set full: {ent['source']}"
+        except Exception:
+            pass
         roof = {"bound": "tensor", "achieved": per_gpu, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": per_gpu / peaks["bf16_tflops"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of one tc_fwd_kernel<128,bf16> launch at B = 512
-                # (ncu --set full, profiles/r1h_ncu_summary.md: 3.2226 GB + 1.0985 GB), scaled by the batch
-                "traffic": 4.3211e9 * Bn / 512.0, "traffic_unit": "bytes per launch (ncu, profiles/r1h_ncu_summary.md)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this batch, from the committed
+                # ncu --set full capture named in profiles/traffic.json (null when no capture matches the kernel + batch)
+                "traffic": traffic, "traffic_unit": traffic_src,
                 "algorithmic_bytes_per_launch": (4.0 * N * D * 2 + 8.0 * N) * Bn,
                 "peak_source": peaks["source"] + " burst (cuBLAS bf16 GEMM)",
                 "frac_of_sustained": per_gpu / peaks["bf16_tflops_sustained"],
                 "frac_of_nominal_2250": per_gpu / 2250.0,
-                "kernel": "tc_fwd_kernel<128,bf16>", "algorithmic_flops_per_launch": FLOPS_PER_BATCH_ELT * Bn,
+                "kernel": kernel_name, "algorithmic_flops_per_launch": FLOPS_PER_BATCH_ELT * Bn,
                 "kernel_ms": ms}
         line = {
             "metric": "dense_fa forward attention TFLOP/s (4*N^2*d*B / time)", "value": value, "unit": "TFLOP/s",

@@ -2,6 +2,10 @@
 // Argument validation mirrors the reference's Julia signatures (same shapes, same defaults,
 // errors instead of MethodError/assertion); dispatch picks the tcgen05 path for 16-bit dense /
 // circulant forward and the exact-fp32 SIMT path otherwise.  There is no CPU fallback.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -472,83 +476,168 @@ struct Arena {
   void* p = nullptr;
   size_t cap = 0;
 };
-Arena g_arena[16];
+constexpr int kMaxDev = 16;
+Arena g_arena[kMaxDev];
 
-struct DevBuf {
-  void* p = nullptr;
-  bool owned = false;
-  ~DevBuf() { if (p && owned) cudaFree(p); }
-  int alloc(size_t n) { owned = true; FA_CUDA_TRY(cudaMalloc(&p, n ? n : 1)); return FA_OK; }
+// The *_host calls run on `device` and put the caller's current device back on every exit path
+// (Julia's CUDA.jl and torch both track the current device per thread).
+struct DeviceGuard {
+  int prev = -1;
+  int rc = FA_OK;
+  explicit DeviceGuard(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); set_error("no CUDA device available (libfa_sm100a has no CPU fallback)"); rc = FA_ERR_CUDA; return; }
+    if (device < 0 || device >= n || device >= kMaxDev) { set_error("device index %d out of range (0..%d)", device, (n < kMaxDev ? n : kMaxDev) - 1); rc = FA_ERR_INVALID; return; }
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaSetDevice");
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Batch-chunked pipeline: H2D of chunk i+1 overlaps the kernels of chunk i and the D2H of
-// chunk i-1 (two streams).  `run(nb, dq, dk, dv, do, dl, dm, stream)` enqueues the kernels.
+// Pageable caller buffers (a plain Julia Array): an async copy from pageable memory is staged by the driver and blocks
+// the host, so nothing overlaps.  Unless FA_FLAG_HOST_NO_REGISTER is set, big pageable buffers are page-locked for the
+// duration of the call (cudaHostRegister) and released on exit.  Already-pinned buffers (cudaHostAlloc, CUDA.pin,
+// torch pin_memory, fa_host_alloc) are used as they are.
+struct HostPins {
+  void* reg[8];
+  int n = 0;
+  void pin(const void* p, size_t bytes) {
+    if (!p || bytes < ((size_t)4 << 20) || n >= 8) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeUnregistered) return;
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) reg[n++] = const_cast<void*>(p);
+    else cudaGetLastError();            // e.g. overlaps a registered range: fall back to the driver's staged copy
+  }
+  ~HostPins() { for (int i = 0; i < n; ++i) cudaHostUnregister(reg[i]); }
+};
+
+// Batch-chunked pipeline on three streams -- host->device copies, kernels, device->host copies -- over three
+// staging buffer sets, so the H2D engine never waits for a kernel or a D2H copy: chunk i+1 (and i+2) stream in while
+// chunk i computes and chunk i-1 streams out.  Every tensor is (.., B) column-major, so a batch chunk is a contiguous
+// byte range of `bytes_per_b * nb`.  `run(nb, din, dout, stream)` enqueues the kernels of one chunk on device copies.
+struct HostIn { const void* h; size_t bytes_per_b; };
+struct HostOut { void* h; size_t bytes_per_b; };
+constexpr int kMaxIO = 8;
+
 template <typename Run>
-int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l, float* m,
-                  size_t q_elems_per_b, size_t v_elems_per_b, size_t stat_per_b, int64_t B, int dtype,
-                  int device, Run run) {
-  int rc = need_device();
-  if (rc) return rc;
-  FA_CUDA_TRY(cudaSetDevice(device));
-  if (device < 0 || device >= 16) { set_error("device index out of range"); return FA_ERR_INVALID; }
-  const size_t esz = dtype_size(dtype);
-  const size_t per_b = (2 * q_elems_per_b + 2 * v_elems_per_b) * esz + 2 * stat_per_b * 4;
-  // The pipeline is bound by the host->device copies (PCIe); what it adds on top is the tail -- kernel and
-  // device->host copy of the LAST chunk -- so big jobs are cut into ~16 chunks (16 MiB .. 256 MiB of tensors each).
+int host_pipeline_n(const HostIn* in, int nin, const HostOut* out, int nout, int64_t B, int flags, int device, Run run) {
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  int rc;
+  size_t per_b = 0;
+  for (int t = 0; t < nin; ++t) per_b += in[t].bytes_per_b;
+  for (int t = 0; t < nout; ++t) per_b += out[t].bytes_per_b;
+  // The pipeline is bound by the host->device copies (PCIe); what it adds on top is the head (first H2D) and the tail
+  // (kernel + D2H of the last chunk), so big jobs are cut into ~24 chunks (16 MiB .. 256 MiB of tensors each).
   int64_t chunk = B;
   const size_t total = per_b * (size_t)B;
-  size_t target = total / 16;
+  size_t target = total / 24;
   if (target < ((size_t)16 << 20)) target = (size_t)16 << 20;
   if (target > ((size_t)256 << 20)) target = (size_t)256 << 20;
   if (total > 2 * target) { chunk = (int64_t)(target / per_b); if (chunk < 1) chunk = 1; }
-  const int nbuf = chunk < B ? 2 : 1;
-  const size_t bq = align256(chunk * q_elems_per_b * esz), bv = align256(chunk * v_elems_per_b * esz), bs = align256(chunk * stat_per_b * 4);
-  const size_t per_set = 2 * bq + 2 * bv + 2 * bs;
+  constexpr int NB = 3;
+  const int64_t nchunks = (B + chunk - 1) / chunk;
+  const int nbuf = nchunks < NB ? (int)nchunks : NB;
+  size_t off_in[kMaxIO], off_out[kMaxIO], per_set = 0;
+  for (int t = 0; t < nin; ++t) { off_in[t] = per_set; per_set += align256(chunk * in[t].bytes_per_b); }
+  for (int t = 0; t < nout; ++t) { off_out[t] = per_set; per_set += align256(chunk * out[t].bytes_per_b); }
+  HostPins pins;
+  if (!(flags & FA_FLAG_HOST_NO_REGISTER) && nchunks > 1) {
+    for (int t = 0; t < nin; ++t) pins.pin(in[t].h, (size_t)B * in[t].bytes_per_b);
+    for (int t = 0; t < nout; ++t) pins.pin(out[t].h, (size_t)B * out[t].bytes_per_b);
+  }
   Arena& ar = g_arena[device];
   std::lock_guard<std::mutex> lock(ar.mu);
   if (ar.cap < per_set * nbuf) {
     if (ar.p) { cudaFree(ar.p); ar.p = nullptr; ar.cap = 0; }
-    FA_CUDA_TRY(cudaMalloc(&ar.p, per_set * nbuf));
-    ar.cap = per_set * nbuf;
+    void* np = nullptr;
+    FA_CUDA_TRY(cudaMalloc(&np, per_set * nbuf));
+    ar.p = np; ar.cap = per_set * nbuf;
   }
-  DevBuf dq[2], dk[2], dvv[2], dout[2], dl[2], dm[2];
-  for (int i = 0; i < nbuf; ++i) {
-    char* base = static_cast<char*>(ar.p) + i * per_set;
-    dq[i].p = base; dk[i].p = base + bq; dvv[i].p = base + 2 * bq; dout[i].p = base + 2 * bq + bv;
-    dl[i].p = base + 2 * bq + 2 * bv; dm[i].p = base + 2 * bq + 2 * bv + bs;
-  }
-  struct Lanes {           // two copy/compute lanes; released on every exit path
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
+  struct Lanes {           // streams and events; drained and released on every exit path
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};                // 0: H2D, 1: kernels, 2: D2H
+    cudaEvent_t in_done[NB] = {}, run_done[NB] = {}, out_done[NB] = {};
     ~Lanes() {
-      for (int i = 0; i < 2; ++i) {
-        if (s[i]) { cudaStreamSynchronize(s[i]); cudaStreamDestroy(s[i]); }
-        if (done[i]) cudaEventDestroy(done[i]);
-      }
+      for (int i = 0; i < 3; ++i) if (s[i]) { cudaStreamSynchronize(s[i]); cudaStreamDestroy(s[i]); }
+      for (int i = 0; i < NB; ++i) { if (in_done[i]) cudaEventDestroy(in_done[i]); if (run_done[i]) cudaEventDestroy(run_done[i]); if (out_done[i]) cudaEventDestroy(out_done[i]); }
     }
-  } lanes;
-  cudaStream_t* s = lanes.s;
-  cudaEvent_t* done = lanes.done;
-  for (int i = 0; i < 2; ++i) { FA_CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)); FA_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); }
-  int it = 0;
-  for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
-    const int i = it % nbuf;
-    const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
-    cudaStream_t st = s[it % 2];
-    if (it >= nbuf) FA_CUDA_TRY(cudaStreamWaitEvent(st, done[i], 0));       // buffer i free again
-    const char* hq = static_cast<const char*>(q) + b0 * q_elems_per_b * esz;
-    const char* hk = static_cast<const char*>(k) + b0 * q_elems_per_b * esz;
-    const char* hv = static_cast<const char*>(v) + b0 * v_elems_per_b * esz;
-    FA_CUDA_TRY(cudaMemcpyAsync(dq[i].p, hq, nb * q_elems_per_b * esz, cudaMemcpyHostToDevice, st));
-    FA_CUDA_TRY(cudaMemcpyAsync(dk[i].p, hk, nb * q_elems_per_b * esz, cudaMemcpyHostToDevice, st));
-    FA_CUDA_TRY(cudaMemcpyAsync(dvv[i].p, hv, nb * v_elems_per_b * esz, cudaMemcpyHostToDevice, st));
-    if ((rc = run(nb, dq[i].p, dk[i].p, dvv[i].p, dout[i].p, static_cast<float*>(dl[i].p), static_cast<float*>(dm[i].p), st))) return rc;
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(o) + b0 * v_elems_per_b * esz, dout[i].p, nb * v_elems_per_b * esz, cudaMemcpyDeviceToHost, st));
-    FA_CUDA_TRY(cudaMemcpyAsync(l + b0 * stat_per_b, dl[i].p, nb * stat_per_b * 4, cudaMemcpyDeviceToHost, st));
-    FA_CUDA_TRY(cudaMemcpyAsync(m + b0 * stat_per_b, dm[i].p, nb * stat_per_b * 4, cudaMemcpyDeviceToHost, st));
-    FA_CUDA_TRY(cudaEventRecord(done[i], st));
+  } ln;
+  for (int i = 0; i < 3; ++i) FA_CUDA_TRY(cudaStreamCreateWithFlags(&ln.s[i], cudaStreamNonBlocking));
+  for (int i = 0; i < nbuf; ++i) {
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ln.in_done[i], cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ln.run_done[i], cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&ln.out_done[i], cudaEventDisableTiming));
   }
-  for (int i = 0; i < 2; ++i) FA_CUDA_TRY(cudaStreamSynchronize(s[i]));
+  int64_t it = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, ++it) {
+    const int i = (int)(it % nbuf);
+    const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    char* base = static_cast<char*>(ar.p) + i * per_set;
+    void *din[kMaxIO], *dout[kMaxIO];
+    for (int t = 0; t < nin; ++t) din[t] = base + off_in[t];
+    for (int t = 0; t < nout; ++t) dout[t] = base + off_out[t];
+    if (it >= nbuf) FA_CUDA_TRY(cudaStreamWaitEvent(ln.s[0], ln.run_done[i], 0));      // inputs of set i consumed
+    for (int t = 0; t < nin; ++t)
+      FA_CUDA_TRY(cudaMemcpyAsync(din[t], static_cast<const char*>(in[t].h) + b0 * in[t].bytes_per_b, nb * in[t].bytes_per_b, cudaMemcpyHostToDevice, ln.s[0]));
+    FA_CUDA_TRY(cudaEventRecord(ln.in_done[i], ln.s[0]));
+    FA_CUDA_TRY(cudaStreamWaitEvent(ln.s[1], ln.in_done[i], 0));
+    if (it >= nbuf) FA_CUDA_TRY(cudaStreamWaitEvent(ln.s[1], ln.out_done[i], 0));     // outputs of set i copied out
+    if ((rc = run(nb, din, dout, ln.s[1]))) return rc;
+    FA_CUDA_TRY(cudaEventRecord(ln.run_done[i], ln.s[1]));
+    FA_CUDA_TRY(cudaStreamWaitEvent(ln.s[2], ln.run_done[i], 0));
+    for (int t = 0; t < nout; ++t)
+      FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out[t].h) + b0 * out[t].bytes_per_b, dout[t], nb * out[t].bytes_per_b, cudaMemcpyDeviceToHost, ln.s[2]));
+    FA_CUDA_TRY(cudaEventRecord(ln.out_done[i], ln.s[2]));
+  }
+  for (int i = 0; i < 3; ++i) FA_CUDA_TRY(cudaStreamSynchronize(ln.s[i]));
+  return FA_OK;
+}
+
+// forward form: inputs q, k, v; outputs o, l, m
+template <typename Run>
+int host_pipeline(const void* q, const void* k, const void* v, void* o, float* l, float* m,
+                  size_t q_elems_per_b, size_t v_elems_per_b, size_t stat_per_b, int64_t B, int dtype,
+                  int flags, int device, Run run) {
+  const size_t esz = dtype_size(dtype);
+  const HostIn in[3] = {{q, q_elems_per_b * esz}, {k, q_elems_per_b * esz}, {v, v_elems_per_b * esz}};
+  const HostOut out[3] = {{o, v_elems_per_b * esz}, {l, stat_per_b * 4}, {m, stat_per_b * 4}};
+  return host_pipeline_n(in, 3, out, 3, B, flags, device, [&](int64_t nb, void** di, void** dout, cudaStream_t st) {
+    return run(nb, di[0], di[1], di[2], dout[0], static_cast<float*>(dout[1]), static_cast<float*>(dout[2]), st);
+  });
+}
+
+// backward form: inputs q, k, v, (o,) dO, l, m; outputs dq, dk, dv.  `ws_bytes(nb)` sizes the per-chunk workspace.
+template <typename Run>
+int host_pipeline_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* l, const float* m,
+                      void* dq, void* dk, void* dvo, size_t q_elems_per_b, size_t v_elems_per_b, size_t stat_per_b,
+                      int64_t B, int dtype, int flags, int device, Run run) {
+  const size_t esz = dtype_size(dtype);
+  HostIn in[7]; int nin = 0;
+  in[nin++] = {q, q_elems_per_b * esz}; in[nin++] = {k, q_elems_per_b * esz}; in[nin++] = {v, v_elems_per_b * esz};
+  const int io = o ? nin : -1;
+  if (o) in[nin++] = {o, v_elems_per_b * esz};
+  const int ig = nin; in[nin++] = {d_o, v_elems_per_b * esz};
+  const int il = nin; in[nin++] = {l, stat_per_b * 4};
+  const int im = nin; in[nin++] = {m, stat_per_b * 4};
+  const HostOut out[3] = {{dq, q_elems_per_b * esz}, {dk, q_elems_per_b * esz}, {dvo, v_elems_per_b * esz}};
+  return host_pipeline_n(in, nin, out, 3, B, flags, device, [&](int64_t nb, void** di, void** dout, cudaStream_t st) {
+    return run(nb, di[0], di[1], di[2], io >= 0 ? di[io] : nullptr, di[ig], static_cast<const float*>(di[il]), static_cast<const float*>(di[im]),
+               dout[0], dout[1], dout[2], st);
+  });
+}
+
+// Per-device workspace for the host entry points (kernels of consecutive chunks are serialised on the pipeline's
+// compute stream, so ONE workspace sized for the largest chunk serves them all); kept like the staging arena.
+struct WsArena { std::mutex mu; void* p = nullptr; size_t cap = 0; };
+WsArena g_ws[kMaxDev];
+int ws_reserve(WsArena& wa, size_t bytes) {
+  if (wa.cap >= bytes) return FA_OK;
+  if (wa.p) { cudaFree(wa.p); wa.p = nullptr; wa.cap = 0; }
+  void* np = nullptr;
+  FA_CUDA_TRY(cudaMalloc(&np, bytes ? bytes : 256));
+  wa.p = np; wa.cap = bytes ? bytes : 256;
   return FA_OK;
 }
 }  // namespace
@@ -560,7 +649,7 @@ int fa_dense_fwd_host(const void* q, const void* k, const void* v, void* o, floa
   int rc = check_common(N, d, dv, B, dtype);
   if (rc) return rc;
   if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  return host_pipeline(q, k, v, o, l, m, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, device,
+  return host_pipeline(q, k, v, o, l, m, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, flags, device,
       [&](int64_t nb, void* dq, void* dk, void* dvp, void* dop, float* dl, float* dm, cudaStream_t st) {
         return fa_dense_fwd(dq, dk, dvp, dop, dl, dm, N, d, dv, nb, dtype, flags, st);
       });
@@ -571,7 +660,7 @@ int fa_circulant_fwd_host(const void* q, const void* k, const void* v, void* o, 
   int rc = check_common(N, d, dv, B, dtype);
   if (rc) return rc;
   if (!q || !k || !v || !o || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  return host_pipeline(q, k, v, o, l, m, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, device,
+  return host_pipeline(q, k, v, o, l, m, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, flags, device,
       [&](int64_t nb, void* dq, void* dk, void* dvp, void* dop, float* dl, float* dm, cudaStream_t st) {
         return fa_circulant_fwd(dq, dk, dvp, dop, dl, dm, N, d, dv, nb, W, dtype, flags, st);
       });
@@ -585,30 +674,148 @@ int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, f
   if (rc) return rc;
   if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
   if (!q || !k || !v || !y || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
-  if ((rc = need_device())) return rc;
-  FA_CUDA_TRY(cudaSetDevice(device));
-  // workspace sized for the largest chunk the pipeline can hand us (<= B)
-  const size_t wsb = fa_workspace_bytes_windowed_fwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags);
-  DevBuf ws[2];
-  if ((rc = ws[0].alloc(wsb))) return rc;
-  if ((rc = ws[1].alloc(wsb))) return rc;
-  int turn = 0;
-  return host_pipeline(q, k, v, y, l, m, (size_t)g.N * d, (size_t)g.N * dv, (size_t)g.WD * g.L, B, dtype, device,
+  if (flags & FA_FLAG_OUT_F32) { set_error("FA_FLAG_OUT_F32 is a device-pointer option"); return FA_ERR_UNSUPPORTED; }
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  const size_t wsb = fa_workspace_bytes_windowed_fwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags);   // largest chunk <= B
+  WsArena& wa = g_ws[device];
+  std::lock_guard<std::mutex> lock(wa.mu);
+  if ((rc = ws_reserve(wa, wsb))) return rc;
+  void* w = wa.p;
+  return host_pipeline(q, k, v, y, l, m, (size_t)g.N * d, (size_t)g.N * dv, (size_t)g.WD * g.L, B, dtype, flags, device,
       [&](int64_t nb, void* dq, void* dk, void* dvp, void* dop, float* dl, float* dm, cudaStream_t st) {
-        void* w = ws[turn++ % 2].p;
         return fa_windowed_fwd(dq, dk, dvp, dop, dl, dm, ndim, dims, d, dv, nb, W, stride, pad, dtype, flags, w, wsb, st);
       });
 }
 
+int fa_dense_bwd_host(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                      const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                      int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags, int device) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !d_o || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (flags & FA_FLAG_OUT_F32) { set_error("FA_FLAG_OUT_F32 is a device-pointer option"); return FA_ERR_UNSUPPORTED; }
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  const size_t wsb = fa_workspace_bytes_dense_bwd(N, d, dv, B, dtype, flags);
+  WsArena& wa = g_ws[device];
+  std::lock_guard<std::mutex> lock(wa.mu);
+  if ((rc = ws_reserve(wa, wsb))) return rc;
+  void* w = wa.p;
+  return host_pipeline_bwd(q, k, v, o, d_o, l, m, dq, dk, dv_out, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, flags, device,
+      [&](int64_t nb, void* a, void* b, void* c, void* oo, void* g, const float* ll, const float* mm, void* x, void* y, void* z, cudaStream_t st) {
+        return fa_dense_bwd(a, b, c, oo, g, ll, mm, x, y, z, N, d, dv, nb, dtype, flags, w, wsb, st);
+      });
+}
+
+int fa_circulant_bwd_host(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                          const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                          int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags, int device) {
+  int rc = check_common(N, d, dv, B, dtype);
+  if (rc) return rc;
+  if (!q || !k || !v || !o || !d_o || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (flags & FA_FLAG_OUT_F32) { set_error("FA_FLAG_OUT_F32 is a device-pointer option"); return FA_ERR_UNSUPPORTED; }
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  const size_t wsb = fa_workspace_bytes_circulant_bwd(N, d, dv, B, W, dtype, flags);
+  WsArena& wa = g_ws[device];
+  std::lock_guard<std::mutex> lock(wa.mu);
+  if ((rc = ws_reserve(wa, wsb))) return rc;
+  void* w = wa.p;
+  return host_pipeline_bwd(q, k, v, o, d_o, l, m, dq, dk, dv_out, (size_t)N * d, (size_t)N * dv, (size_t)N, B, dtype, flags, device,
+      [&](int64_t nb, void* a, void* b, void* c, void* oo, void* g, const float* ll, const float* mm, void* x, void* y, void* z, cudaStream_t st) {
+        return fa_circulant_bwd(a, b, c, oo, g, ll, mm, x, y, z, N, d, dv, nb, W, dtype, flags, w, wsb, st);
+      });
+}
+
+int fa_windowed_bwd_host(const void* q, const void* k, const void* v, const void* d_y,
+                         const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                         int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int dtype, int flags, int device) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
+  if (!q || !k || !v || !d_y || !l || !m || !dq || !dk || !dv_out) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if (flags & FA_FLAG_OUT_F32) { set_error("FA_FLAG_OUT_F32 is a device-pointer option"); return FA_ERR_UNSUPPORTED; }
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  const size_t wsb = fa_workspace_bytes_windowed_bwd(ndim, dims, d, dv, B, W, stride, pad, dtype, flags);
+  WsArena& wa = g_ws[device];
+  std::lock_guard<std::mutex> lock(wa.mu);
+  if ((rc = ws_reserve(wa, wsb))) return rc;
+  void* w = wa.p;
+  return host_pipeline_bwd(q, k, v, nullptr, d_y, l, m, dq, dk, dv_out, (size_t)g.N * d, (size_t)g.N * dv, (size_t)g.WD * g.L, B, dtype, flags, device,
+      [&](int64_t nb, void* a, void* b, void* c, void*, void* gy, const float* ll, const float* mm, void* x, void* y, void* z, cudaStream_t st) {
+        return fa_windowed_bwd(a, b, c, gy, ll, mm, x, y, z, ndim, dims, d, dv, nb, W, stride, pad, dtype, flags, w, wsb, st);
+      });
+}
+
+// Page-locked host memory placed on the NUMA node of `device` (its PCIe root): the thread is bound to the device's
+// local CPUs (sysfs local_cpulist of the PCI function) while the pages are allocated and first touched, then its
+// affinity is restored.  Host buffers allocated this way keep every H2D / D2H copy off the inter-socket link, which
+// is what caps the aggregate rate when all 8 GPUs of a box stream from host memory at once.
+int fa_host_alloc(void** out, size_t bytes, int device) {
+  if (!out || bytes == 0) { set_error("fa_host_alloc: bad arguments"); return FA_ERR_INVALID; }
+  *out = nullptr;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  cpu_set_t old_set, new_set;
+  bool bound = false;
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) == cudaSuccess && sched_getaffinity(0, sizeof(old_set), &old_set) == 0) {
+    for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    if (FILE* f = fopen(path, "r")) {
+      char line[1024] = "";
+      if (fgets(line, sizeof(line), f)) {
+        CPU_ZERO(&new_set);
+        int n_set = 0;
+        for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+          int a = 0, b = 0;
+          const int got = sscanf(tok, "%d-%d", &a, &b);
+          if (got == 1) b = a;
+          if (got >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &old_set)) { CPU_SET(c, &new_set); ++n_set; }
+        }
+        if (n_set > 0 && sched_setaffinity(0, sizeof(new_set), &new_set) == 0) bound = true;
+      }
+      fclose(f);
+    }
+  } else cudaGetLastError();
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (e == cudaSuccess) {                                   // first touch under the binding (cudaHostAlloc usually has, be sure)
+    volatile char* c = static_cast<volatile char*>(p);
+    for (size_t off = 0; off < bytes; off += 4096) c[off] = 0;
+  }
+  if (bound) sched_setaffinity(0, sizeof(old_set), &old_set);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+  *out = p;
+  return FA_OK;
+}
+
+int fa_host_free(void* p) {
+  if (!p) return FA_OK;
+  FA_CUDA_TRY(cudaFreeHost(p));
+  return FA_OK;
+}
+
 int fa_release_host_staging(void) {
-  for (int d = 0; d < 16; ++d) {
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+  for (int d = 0; d < kMaxDev; ++d) {
     std::lock_guard<std::mutex> lock(g_arena[d].mu);
-    if (g_arena[d].p) {
+    std::lock_guard<std::mutex> lock2(g_ws[d].mu);
+    if (g_arena[d].p || g_ws[d].p) {
       cudaSetDevice(d);
-      cudaFree(g_arena[d].p);
+      if (g_arena[d].p) cudaFree(g_arena[d].p);
+      if (g_ws[d].p) cudaFree(g_ws[d].p);
       g_arena[d].p = nullptr; g_arena[d].cap = 0;
+      g_ws[d].p = nullptr; g_ws[d].cap = 0;
     }
   }
+  if (prev >= 0) cudaSetDevice(prev);
   return FA_OK;
 }
 

@@ -29,7 +29,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 __all__ = [
-    "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "FA_FLAG_OUT_F32", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
+    "lib", "FaError", "FA_FLAG_FORCE_SIMT", "FA_FLAG_BF16_INTERNALS", "FA_FLAG_OUT_F32", "FA_FLAG_HOST_NO_REGISTER", "jl_host_empty", "jl_empty", "jl_array", "jl_randn", "is_jl_contiguous", "last_path",
     "dense_fa", "dense_fa_", "dense_fa_backward", "windowed_fa", "windowed_fa_backward", "block_fa",
     "circulant_fa", "circulant_fa_", "circulant_fa_backward", "fused_softmax", "fused_softmax_",
     "window", "unwindow", "window_index", "window_count", "cartesian_circulant", "circulant_keys", "circulant2d_keys", "circulant", "batch_circulant",
@@ -43,6 +43,7 @@ FA_F32, FA_F16, FA_BF16 = 0, 1, 2
 FA_FLAG_FORCE_SIMT = 1
 FA_FLAG_BF16_INTERNALS = 2
 FA_FLAG_OUT_F32 = 4          # 16-bit inputs, float32 outputs (fp32 accumulators stored unrounded; tcgen05 kernels only)
+FA_FLAG_HOST_NO_REGISTER = 8  # *_host entry points: do not page-lock pageable caller buffers for the call
 _DTYPES = {torch.float32: FA_F32, torch.float16: FA_F16, torch.bfloat16: FA_BF16}
 
 
@@ -91,6 +92,11 @@ def _load():
         "fa_dense_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, ci]),
         "fa_circulant_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, i64, ci, ci, ci]),
         "fa_windowed_fwd_host": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, ci]),
+        "fa_dense_bwd_host": (ci, [vp] * 10 + [i64, i64, i64, i64, ci, ci, ci]),
+        "fa_circulant_bwd_host": (ci, [vp] * 10 + [i64, i64, i64, i64, i64, ci, ci, ci]),
+        "fa_windowed_bwd_host": (ci, [vp] * 9 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, ci]),
+        "fa_host_alloc": (ci, [ctypes.POINTER(vp), sz, ci]),
+        "fa_host_free": (ci, [vp]),
         "fa_release_host_staging": (ci, []),
         "fa_shard_batch": (ci, [i64, ci, ci, pi64, pi64]),
         "fa_merge_partials": (ci, [vp] * 7 + [i64, i64, i64, ci, ci, vp]),
@@ -114,7 +120,8 @@ EXPORTED_SYMBOLS = (
     "fa_circulant_fwd_host fa_windowed_fwd_host fa_release_host_staging fa_shard_batch fa_merge_partials "
     "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd "
     "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd "
-    "fa_workspace_bytes_circulant2d_bwd_ex fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd").split()
+    "fa_workspace_bytes_circulant2d_bwd_ex fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd "
+    "fa_dense_bwd_host fa_circulant_bwd_host fa_windowed_bwd_host fa_host_alloc fa_host_free").split()
 
 
 def _check(rc: int, what: str):
@@ -134,6 +141,36 @@ def jl_empty(shape: Sequence[int], dtype=torch.float32, device="cuda") -> torch.
     """``Array{T}(undef, shape...)``: tensor of Julia shape ``shape`` with column-major strides."""
     shape = tuple(int(s) for s in shape)
     t = torch.empty(shape[::-1], dtype=dtype, device=device)
+    return t.permute(*range(len(shape) - 1, -1, -1))
+
+
+class _HostBlock:
+    """Owner of one fa_host_alloc allocation (freed when the last tensor viewing it dies)."""
+    def __init__(self, nbytes: int, device: int):
+        p = ctypes.c_void_p()
+        _check(lib.fa_host_alloc(ctypes.byref(p), nbytes, int(device)), "fa_host_alloc")
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib.fa_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def jl_host_empty(shape: Sequence[int], dtype=torch.float32, device: int = 0) -> torch.Tensor:
+    """Column-major HOST tensor of Julia shape ``shape`` in page-locked memory on the NUMA node of GPU ``device``
+    (``fa_host_alloc``): the fastest source / destination for the ``*_host`` entry points."""
+    import numpy as np
+    shape = tuple(int(s) for s in shape)
+    n = 1
+    for s_ in shape:
+        n *= s_
+    esz = torch.empty((), dtype=dtype).element_size()
+    blk = _HostBlock(max(n * esz, 1), device)
+    raw = (ctypes.c_uint8 * blk.nbytes).from_address(blk.ptr)
+    raw._fa_block = blk                    # storage -> numpy array -> ctypes buffer -> block: freed with the last view
+    arr = np.frombuffer(raw, dtype=np.uint8)
+    t = torch.from_numpy(arr).view(dtype)[:n].reshape(shape[::-1])
     return t.permute(*range(len(shape) - 1, -1, -1))
 
 
@@ -290,6 +327,10 @@ def dense_fa_backward(Q, K, V, O, dO, l, m, flags: int = 0):
     dv = int(V.shape[-2])
     l, m = (jl_array(t, torch.float32) for t in (l, m))
     dQ, dK, dV = (jl_empty(t.shape, _out_dtype(t, flags), t.device) for t in (Q, K, V))
+    if not Q.is_cuda:                                        # the reference's Array arguments (src/dense.jl:104-111)
+        _check(lib.fa_dense_bwd_host(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m), _ptr(dQ), _ptr(dK), _ptr(dV),
+                                     N, d, dv, B, _dt(Q), flags, _cur_dev()), "fa_dense_bwd_host")
+        return dQ, dK, dV
     ws = _workspace(lib.fa_workspace_bytes_dense_bwd(N, d, dv, B, _dt(Q), flags), Q.device)
     with torch.cuda.device(Q.device):
         _check(lib.fa_dense_bwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m),
@@ -451,6 +492,10 @@ def windowed_fa_backward(q, k, v, dy, l, m, windowsize: int, stride=None, pad=No
     d, dv, B = int(q.shape[-2]), int(v.shape[-2]), int(q.shape[-1])
     dims = _i64arr(spatial)
     dq, dk, dvv = (jl_empty(t.shape, _out_dtype(t, flags), t.device) for t in (q, k, v))
+    if not q.is_cuda:
+        _check(lib.fa_windowed_bwd_host(_ptr(q), _ptr(k), _ptr(v), _ptr(dy), _ptr(l), _ptr(m), _ptr(dq), _ptr(dk), _ptr(dvv),
+                                        len(spatial), dims, d, dv, B, W, stride, pad, _dt(q), flags, _cur_dev()), "fa_windowed_bwd_host")
+        return dq, dk, dvv
     ws = _workspace(lib.fa_workspace_bytes_windowed_bwd(len(spatial), dims, d, dv, B, W, stride, pad, _dt(q), flags), q.device)
     with torch.cuda.device(q.device):
         _check(lib.fa_windowed_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(dy), _ptr(l), _ptr(m), _ptr(dq), _ptr(dk), _ptr(dvv),
@@ -653,6 +698,10 @@ def circulant_fa_backward(Q, K, V, O, dO, l, m, W: int, flags: int = 0):
     N, d, B = (int(s) for s in Q.shape)
     dv = int(V.shape[1])
     dQ, dK, dV = (jl_empty(t.shape, _out_dtype(t, flags), t.device) for t in (Q, K, V))
+    if not Q.is_cuda:
+        _check(lib.fa_circulant_bwd_host(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m), _ptr(dQ), _ptr(dK), _ptr(dV),
+                                         N, d, dv, B, int(W), _dt(Q), flags, _cur_dev()), "fa_circulant_bwd_host")
+        return dQ, dK, dV
     ws = _workspace(lib.fa_workspace_bytes_circulant_bwd(N, d, dv, B, int(W), _dt(Q), flags), Q.device)
     with torch.cuda.device(Q.device):
         _check(lib.fa_circulant_bwd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(l), _ptr(m),

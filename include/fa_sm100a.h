@@ -63,6 +63,9 @@ typedef enum fa_dtype {
                                     the shape falls to the exact-fp32 kernels, no-op for Float32 inputs.  Windowed calls
                                     then need the workspace fa_workspace_bytes_windowed_* report for these flags. */
 
+#define FA_FLAG_HOST_NO_REGISTER 8 /* *_host entry points: do not page-lock pageable caller buffers for the call
+                                    (cudaHostRegister); the driver's staged, host-blocking copies are used instead */
+
 /* ---- host helpers -------------------------------------------------------------------- */
 int fa_version(void);                       /* FA_VERSION_MAJOR*100 + FA_VERSION_MINOR     */
 const char* fa_last_error_string(void);     /* thread-local, never NULL                    */
@@ -183,6 +186,25 @@ int fa_circulant_fwd_host(const void* q, const void* k, const void* v, void* o, 
 int fa_windowed_fwd_host(const void* q, const void* k, const void* v, void* y, float* l, float* m,
                          int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
                          int64_t W, int64_t stride, int64_t pad, int dtype, int flags, int device);
+
+/* backward with HOST buffers: the reference's dense_fa_backward(Q,K,V,O,dO,l,m) takes Arrays (src/dense.jl:104-111).
+ * Same batch-chunked three-stream pipeline; the workspace is kept inside the library per device. */
+int fa_dense_bwd_host(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                      const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                      int64_t N, int64_t d, int64_t dv, int64_t B, int dtype, int flags, int device);
+int fa_circulant_bwd_host(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                          const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                          int64_t N, int64_t d, int64_t dv, int64_t B, int64_t W, int dtype, int flags, int device);
+int fa_windowed_bwd_host(const void* q, const void* k, const void* v, const void* d_y,
+                         const float* l, const float* m, void* dq, void* dk, void* dv_out,
+                         int ndim, const int64_t* dims, int64_t d, int64_t dv, int64_t B,
+                         int64_t W, int64_t stride, int64_t pad, int dtype, int flags, int device);
+/* The *_host calls run on `device` and restore the caller's current device before returning.  Pageable caller
+ * buffers are page-locked for the duration of a multi-chunk call (cudaHostRegister; FA_FLAG_HOST_NO_REGISTER skips
+ * that); buffers from fa_host_alloc -- page-locked AND placed on the NUMA node of `device` -- avoid both the
+ * registration cost and inter-socket traffic. */
+int fa_host_alloc(void** out, size_t bytes, int device);
+int fa_host_free(void* p);
 
 /* ---- multi-GPU ------------------------------------------------------------------
  * The path shards over the trailing batch*head dim (contiguous in memory, src/dense.jl:6-8,45) with no

@@ -6,9 +6,11 @@ bench/compare.jl:20,47,74, plus backward and the edge cases of SURV
 Tolerances (BASELINE.json north_star): 1e-5 for the exact-fp32 path, 2e-3 for bf16/fp16
 compute with fp32 accumulation; both as max-abs error relative to max-abs of the oracle.
 16-bit cases feed GPU and oracle the same Float32 values (pre-rounded so they are exactly
-representable), and results that are STORED in a 16-bit type are allowed that type's own
-round-to-nearest half-ulp on top of the compute tolerance (util.rel_err, `storage=`): bf16
-storage alone can be off by 2^-8 = 3.9e-3, which no kernel can avoid.
+representable), and results that are STORED in bf16 are allowed bf16's own round-to-nearest
+half-ulp on top of the compute tolerance (util.rel_err, `storage=`): bf16 storage alone can be off
+by 2^-8 = 3.9e-3, which no kernel can avoid.  fp16 results get NO allowance (2e-3 as stored), and
+tests/test_gpu_parity_r2.py proves the bf16 COMPUTE error under 2e-3 with no allowance through
+FA_FLAG_OUT_F32 (fp32 accumulators stored unrounded).
 """
 import numpy as np
 import pytest
@@ -76,7 +78,7 @@ def test_dense_fwd_16bit_simt_fallback(dtype):
         y0, l0, m0 = fo.dense_fa(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64))
         y, l, m = fa.dense_fa(*(to_dev(t, dtype) for t in (q, k, v)))
         assert fa.last_path() == "simt"
-        assert rel_err(to_np(y), y0, dtype) < 1e-5 and rel_err(to_np(l), l0) < 1e-4
+        assert rel_err(to_np(y), y0, dtype, exact_math=True) < 1e-5 and rel_err(to_np(l), l0) < 1e-4
 
 
 def test_dense_fwd_tc_large_logits_rescale():
@@ -492,9 +494,12 @@ def test_autograd_wrappers_match_oracle_gradients(dtype):
     Q, K, V = (to_dev(t, dtype).requires_grad_() for t in (q, k, v))
     y = fag.dense_attention(Q, K, V)
     (y.float() * to_dev(g, dtype).float()).sum().backward()
-    want = fo.dense_backward(*(t.astype(np.float64) for t in (q, k, v, g)))
+    # expectation on the saved (O, l, m) of the forward -- the OneDFastBack signature
+    r3 = lambda t: np.reshape(t, (-1,) + t.shape[-2:], order="F")
+    y_, l_, m_ = fa.dense_fa(Q.detach(), K.detach(), V.detach())
+    want = fo.dense_fa_backward_blocked(*(r3(t.astype(np.float64)) for t in (q, k, v)), r3(to_np(y_)), r3(g.astype(np.float64)), to_np(l_), to_np(m_))
     for got, w in zip((Q.grad, K.grad, V.grad), want):
-        assert rel_err(to_np(got).reshape(w.shape, order="F"), w, dtype) < max(tol, 3e-3 if dtype == BF16 else 0)
+        assert rel_err(r3(to_np(got)), w, dtype) < tol
     # windowed 2-D and circulant 1-D
     shape = (20, 12, 64, 2)
     q, k, v, g = (randn_np(shape, s, dtype) for s in range(4))
@@ -509,9 +514,10 @@ def test_autograd_wrappers_match_oracle_gradients(dtype):
     Q, K, V = (to_dev(t, dtype).requires_grad_() for t in (q, k, v))
     y = fag.circulant_attention(Q, K, V, 33)
     (y.float() * to_dev(g, dtype).float()).sum().backward()
-    want = fo.circulant_backward(*(t.astype(np.float64) for t in (q, k, v, g)), 33)
+    O_, l_, m_ = fa.circulant_fa(Q.detach(), K.detach(), V.detach(), 33)
+    want = fo.circulant_backward_given(*(t.astype(np.float64) for t in (q, k, v)), to_np(O_), g.astype(np.float64), to_np(l_), to_np(m_), 33)
     for got, w in zip((Q.grad, K.grad, V.grad), want):
-        assert rel_err(to_np(got), w, dtype) < max(tol, 3e-3 if dtype == BF16 else 0)
+        assert rel_err(to_np(got), w, dtype) < tol
 
 
 # ------------------------------------------------------------------------------- 2-D circulant
@@ -527,7 +533,9 @@ def test_circulant2d_fwd_bwd(X, Y, d, B, W, dtype):
     assert rel_err(to_np(O), O0, dtype) < tol and rel_err(to_np(l), l0) < 1e-5 and rel_err(to_np(m), m0) < 1e-5
     want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
     got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
-    btol = 1e-5 if dtype == F32 else 3e-3          # D = rowsum(dO o O) from the bf16-stored O
+    if dtype != F32:                               # 16-bit O: expectation on the saved (O, l, m)
+        want = fo.circulant2d_backward_given(*(t.astype(np.float64) for t in (q, k, v)), to_np(O), g.astype(np.float64), to_np(l), to_np(m), W)
+    btol = 1e-5 if dtype == F32 else 1e-4
     for a, b_ in zip(got, want):
         assert rel_err(to_np(a), b_, dtype) < btol
 
@@ -550,11 +558,11 @@ def test_circulant2d_fwd_tc(X, Y, B, W, dtype):
     assert rel_err(to_np(O), O0, dtype) < 2e-3
     assert rel_err(to_np(l), l0) < 2e-3
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
-    want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
+    want = fo.circulant2d_backward_given(*(t.astype(np.float64) for t in (q, k, v)), to_np(O), g.astype(np.float64), to_np(l), to_np(m), W)
     got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
     assert fa.last_path() == "tc"                       # the 1-D circulant tcgen05 backward kernels walking W image rows
     for a, b_ in zip(got, want):
-        assert rel_err(to_np(a), b_, dtype) < 4e-3      # D = rowsum(dO o O) from the 16-bit O, P from the 16-bit-compute (l, m)
+        assert rel_err(to_np(a), b_, dtype) < 2e-3      # on the saved (O, l, m), the OneDFastBack signature
     simt = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W, flags=fa.FA_FLAG_FORCE_SIMT)
     assert fa.last_path() == "simt"
     for a, b_ in zip(got, simt):                        # same inputs incl. the stored (O, l, m): the two families agree to 2e-3
@@ -574,9 +582,9 @@ def test_circulant2d_fwd_bwd_tc_d128(X, Y, B, W):
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
     got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
     assert fa.last_path() == "tc"
-    want = fo.circulant2d_backward(*(t.astype(np.float64) for t in (q, k, v, g)), W)
+    want = fo.circulant2d_backward_given(*(t.astype(np.float64) for t in (q, k, v)), to_np(O), g.astype(np.float64), to_np(l), to_np(m), W)
     for a, b_ in zip(got, want):
-        assert rel_err(to_np(a), b_, dtype) < 4e-3
+        assert rel_err(to_np(a), b_, dtype) < 2e-3
 
 
 def test_circulant2d_rejects_bad_window():
