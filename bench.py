@@ -344,15 +344,17 @@ def main():
             cover = torch.tensor([planes, plan.nwin], device=dev, dtype=torch.int64)
             dist.all_reduce(cover)
             one = None
-            gq = [torch.empty(0, device=dev)]
             shapes = [None] * world
             dist.all_gather_object(shapes, planes)
+            maxp = max(shapes)
             parts = {}
-            for name, t_ in (("q", sq), ("k", sk), ("v", sv)):                        # gather the slabs on every rank (check only)
-                bufs = [torch.empty(1, 64, shapes[r], S3, S3, dtype=bf, device=dev) for r in range(world)]
-                dist.all_gather(bufs, t_.permute(4, 3, 2, 1, 0).contiguous())
-                parts[name] = fa.jl_array(torch.cat(bufs, dim=2).permute(4, 3, 2, 1, 0)) if rank == 0 else None
-                del bufs
+            for name, t_ in (("q", sq), ("k", sk), ("v", sv)):                        # gather the slabs (check only, untimed)
+                mine = torch.zeros(1, 64, maxp, S3, S3, dtype=bf, device=dev)         # equal-sized pieces for all_gather
+                mine[:, :, :planes].copy_(t_.permute(4, 3, 2, 1, 0))
+                bufs = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(bufs, mine)
+                parts[name] = fa.jl_array(torch.cat([b_[:, :, :shapes[r]] for r, b_ in enumerate(bufs)], dim=2).permute(4, 3, 2, 1, 0)) if rank == 0 else None
+                del bufs, mine
             if rank == 0:
                 fy, fl_, fm_ = fa.windowed_fa(parts["q"], parts["k"], parts["v"], 5, 5, 3)
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
