@@ -924,9 +924,10 @@ typedef CUresult (*EncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 5-D map over one (X, Y, Z, d, B) tensor (missing spatial dims = 1): box (BX, by, bz, d, 1), no swizzle,
+// 5-D map over one (X, Y, Z, d, B) tensor (missing spatial dims = 1): box (BX, by, bz, CH, 1), no swizzle,
 // zero fill out of bounds (= the zero padding of `window`, src/utils.jl:40)
-int make_win_tmap(CUtensorMap* tm, const void* base, int dtype, const Geo& g, int D, const TmaGeo& tg) {
+}  // namespace
+int make_win_tmap_box(CUtensorMap* tm, const void* base, int dtype, const Geo& g, int D, int BX, int by, int bz, int CH) {
   static EncodeTiledFn5 fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -938,13 +939,17 @@ int make_win_tmap(CUtensorMap* tm, const void* base, int dtype, const Geo& g, in
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return FA_ERR_CUDA; }
   const cuuint64_t dims[5] = {(cuuint64_t)g.s[0], (cuuint64_t)g.s[1], (cuuint64_t)g.s[2], (cuuint64_t)D, (cuuint64_t)g.B};
   const cuuint64_t strides[4] = {(cuuint64_t)g.s[0] * 2, (cuuint64_t)g.s[0] * g.s[1] * 2, (cuuint64_t)g.N * 2, (cuuint64_t)g.N * D * 2};
-  const cuuint32_t box[5] = {(cuuint32_t)tg.BX, (cuuint32_t)tg.by, (cuuint32_t)tg.bz, (cuuint32_t)tg.CH, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)BX, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)CH, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapDataType dt = dtype == FA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(tm, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (windowed 5-D) failed (CUresult %d)", (int)r); return FA_ERR_CUDA; }
   return FA_OK;
+}
+namespace {
+int make_win_tmap(CUtensorMap* tm, const void* base, int dtype, const Geo& g, int D, const TmaGeo& tg) {
+  return make_win_tmap_box(tm, base, dtype, g, D, tg.BX, tg.by, tg.bz, tg.CH);
 }
 
 // can the TMA-gather variant take this geometry?  (exact-cover windows, 16-byte aligned rows, box fits the staging)
@@ -1069,9 +1074,25 @@ bool tc_win_supported(const Geo& g, int dtype) {
   return make_map(g, 2, mp);
 }
 
+bool tc_winx_supported(const Geo& g, const FwdArgs& a, int dtype);
+int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
+
 int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   if (!tc_win_supported(g, dtype)) { set_error("tc_win_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
   const int fmt = dtype == FA_BF16 ? 1 : 0;
+  // large exact-cover problems: the streamed kernel of fa_tc_winx.cu (TMA boxes + 16-byte repack, four tiles per SM).
+  // FA_WINX = 0 never, 1 whenever it applies, unset: when every SM gets at least four of its groups
+  {
+    static const int winx = [] { const char* e = getenv("FA_WINX"); return e ? atoi(e) : -1; }();
+    if (winx != 0 && tc_winx_supported(g, a, dtype)) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int nwc = 4 * (128 / g.WD);
+      const long long groups = (long long)((g.o[0] + nwc - 1) / nwc) * g.o[1] * g.o[2] * g.B;
+      if (winx == 1 || groups >= 4LL * sms) return tc_winx_fwd(g, a, dtype, st);
+    }
+  }
   if (g.d == 128) return fmt ? launch_win_fwd<128, 1, 1>(g, a, st) : launch_win_fwd<128, 1, 0>(g, a, st);
   // d = 64: two 128-row tiles per CTA (2 CTAs / SM; longer x-runs per gather) or one tile per CTA (3 CTAs / SM).
   // Small problems -- fewer than two pair-groups per resident CTA -- are latency bound and take the finer split

@@ -1,0 +1,489 @@
+// fa_tc_winx.cu -- streamed tcgen05 windowed attention forward for sm_100a (round 2): windowed_fa / block_fa
+// (reference src/windowed.jl:1-23, window / unwindow of src/utils.jl:36-54 fused in) for exact-cover windows
+// (stride == W), d = dv = 64, 16-bit inputs.  Replaces the per-thread 2-byte gather of fa_tc_win.cu, which the
+// round-1 profile showed bound by the L1 data pipe (every (channel, y, z) line of the volume is touched for 10-14
+// useful bytes), on the large problems; fa_tc_win.cu stays for everything this kernel does not take.
+//
+// One persistent 512-thread CTA per SM works on GROUPS of nwc = 4 * G x-adjacent windows (G = floor(128 / W^D)
+// windows per 128-row tile, four tiles, all 512 TMEM columns):
+//   * q, k, v arrive as 5-D TMA boxes (x: the group's tokens rounded out to 16-byte boundaries, y: W, z: W,
+//     16 channels, 1 batch element) through a ring of three 25 KB staging slots -- full 32-byte sectors, no load
+//     instructions, zero fill outside the volume = the zero padding of `window`.  The boxes of a group are a
+//     stream Q0 K0 Q1 K1 Q2 K2 Q3 K3 V0 V1 V2 V3 (16-channel slices); the stream runs up to three boxes ahead of the
+//     consumer, i.e. into the next group while this one is in its softmax / output phases.
+//   * repack staging -> operand tiles: one thread produces one 16-byte chunk (8 consecutive tile rows of one
+//     channel) of the canonical SWIZZLE_128B [channel][token] layout with 8 two-byte shared loads and ONE 16-byte
+//     conflict-free shared store (round 1: one 2-byte global load + one 2-byte shared store per element).
+//   * S = Q K^T is issued slice by slice (K = 16 channels per tcgen05.mma) as soon as the Q and K slices are
+//     repacked, so the tensor work hides under the repack; V reuses the Q tiles once S is complete.
+//   * softmax as in fa_tc_win.cu (thread == row, block-diagonal mask, 32-column chunks classified per warp).
+//   * O rows are converted and staged in the volume's own order [channel][y, z row][x] over the dead K tiles and
+//     written with 4-byte stores along x across all windows of the group (40-byte runs instead of 10-byte ones).
+// HBM-bound by design: q, k, v read once, y written once; L2 -> SM traffic is the box overfetch (1.2-1.6x).
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include "fa_common.cuh"
+#include "fa_ptx.cuh"
+
+namespace fa {
+int make_win_tmap_box(CUtensorMap* tm, const void* base, int dtype, const Geo& g, int D, int BX, int by, int bz, int CH);
+
+namespace {
+using namespace ptx;
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+template <int FMT> struct El { using type = __half; };
+template <> struct El<1> { using type = __nv_bfloat16; };
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if (FMT == 1) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t cvt16(float a) { return pack16<FMT>(a, 0.f) & 0xffffu; }
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+struct XCfg {
+  static constexpr int D = 64;
+  static constexpr int NT = 4;                               // 128-row tiles per CTA = all 512 TMEM columns
+  static constexpr int THREADS = 128 * NT;
+  static constexpr int CH = 16;                              // channels per TMA box = one tcgen05.mma K step
+  static constexpr int NCS = D / CH;
+  static constexpr int BOXES = 3 * NCS;                      // boxes per group: Q0 K0 .. Q3 K3 V0 .. V3
+  static constexpr int BOX_BYTES = 64 * D * 2;               // one 64-token block of an operand tile
+  static constexpr int TILE_BYTES = 2 * BOX_BYTES;           // 16 KB
+  static constexpr int OFF_TQ = 0;                           // [NT] Q tiles, later V tiles
+  static constexpr int OFF_TK = NT * TILE_BYTES;             // [NT] K tiles, later the output staging
+  static constexpr int NSLOT = 3;
+  static constexpr int SLOT_BYTES = 25600;                   // >= BX * RG * CH * 2
+  static constexpr int OFF_ST = 2 * NT * TILE_BYTES;
+  static constexpr int OFF_ROWTAB = OFF_ST + NSLOT * SLOT_BYTES;   // uint32[128]: static (rowidx << 16 | column) of a tile row
+  static constexpr int OFF_ROWOFF = OFF_ROWTAB + 128 * 4;          // int[64]: global token offset of every (y, z) row of the group, -1 = padding
+  static constexpr int OFF_BAR = OFF_ROWOFF + 64 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+struct XParams {
+  const void *q, *k, *v;
+  void* y;
+  float *l, *m;
+  Geo g;
+  int G, nwc, TW, RG;          // windows per tile / per group, tokens per (y, z) row of a group, rows per window
+  int gpr;                     // groups per window row
+  int BXs, BXl;                // box extents along x (tokens): small when shift + TW fits, large otherwise
+  int NP;                      // 4-byte store pieces per output run
+  unsigned magicNP;            // ceil(2^32 / NP)
+  long long ngroups;
+  float scale_log2;
+};
+
+struct GroupInfo {
+  long long gw0;               // linear index (batch included) of the group's first window
+  int nvalid;                  // windows of the group that exist (the last group of a window row may be short)
+  int x0, y0, z0, b;           // first token of the group per dim (may be negative = padding), batch element
+  int shift, BX;               // x0 - box start (0..7), box extent used
+};
+
+__device__ __forceinline__ GroupInfo decode_group(const XParams& prm, long long grp) {
+  const Geo& g = prm.g;
+  GroupInfo gi;
+  const long long rowi = grp / prm.gpr;
+  const int gix = (int)(grp - rowi * prm.gpr);
+  const int wx0 = gix * prm.nwc;
+  gi.nvalid = g.o[0] - wx0 < prm.nwc ? g.o[0] - wx0 : prm.nwc;
+  const int wy = (int)(rowi % g.o[1]);
+  const long long r2 = rowi / g.o[1];
+  const int wz = (int)(r2 % g.o[2]);
+  gi.b = (int)(r2 / g.o[2]);
+  gi.gw0 = (((long long)gi.b * g.o[2] + wz) * g.o[1] + wy) * g.o[0] + wx0;
+  gi.x0 = wx0 * g.stride - g.padv[0];
+  gi.y0 = g.nd >= 2 ? wy * g.stride - g.padv[1] : 0;
+  gi.z0 = g.nd >= 3 ? wz * g.stride - g.padv[2] : 0;
+  gi.shift = (gi.x0 + 1024) & 7;
+  gi.BX = (gi.shift + gi.nvalid * g.W <= prm.BXs) ? prm.BXs : prm.BXl;
+  return gi;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(XCfg::THREADS, 1)
+tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_constant__ CUtensorMap tk_s,
+                   const __grid_constant__ CUtensorMap tv_s, const __grid_constant__ CUtensorMap tq_l,
+                   const __grid_constant__ CUtensorMap tk_l, const __grid_constant__ CUtensorMap tv_l,
+                   const XParams prm) {
+  using C = XCfg;
+  using T = typename El<FMT>::type;
+  constexpr int D = C::D;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sptr);
+  uint32_t* rowtab = reinterpret_cast<uint32_t*>(sptr + C::OFF_ROWTAB);
+  int* rowoff = reinterpret_cast<int*>(sptr + C::OFF_ROWOFF);
+  const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16, bar_full = bar_s + 32;   // bar_full[NSLOT]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const Geo& g = prm.g;
+  const long long N = g.N;
+  const int W = g.W, WD = g.WD, RG = prm.RG, TW = prm.TW;
+
+  if (tid == 0) {
+    mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    for (int i = 0; i < C::NSLOT; ++i) mbar_init(bar_full + 8 * i, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tq_s); prefetch_tensormap(&tk_s); prefetch_tensormap(&tv_s);
+    prefetch_tensormap(&tq_l); prefetch_tensormap(&tk_l); prefetch_tensormap(&tv_l);
+  }
+  // static table of a tile row: which (y, z) row of the window and which column of the group's x-range it reads
+  if (tid < 128) {
+    const int r = tid;
+    uint32_t e = 0xffffffffu;
+    if (r < prm.G * WD) {
+      const int wi = r / WD, slot = r - wi * WD;
+      const int rowidx = slot / W, kx = slot - rowidx * W;
+      e = ((uint32_t)rowidx << 16) | (uint32_t)(wi * W + kx);
+    }
+    rowtab[r] = e;
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // ---- the TMA stream: box number `pos` of this CTA = box (pos % BOXES) of its (pos / BOXES)-th group -> slot pos % NSLOT
+  auto issue_box = [&](uint32_t pos) {
+    const long long grp = (long long)blockIdx.x + (long long)(pos / C::BOXES) * gridDim.x;
+    if (grp >= prm.ngroups) return;
+    const int j = (int)(pos % C::BOXES);
+    const int x = j < 2 * C::NCS ? (j & 1) : 2, cs = j < 2 * C::NCS ? (j >> 1) : j - 2 * C::NCS;
+    const GroupInfo gi = decode_group(prm, grp);
+    const bool small = gi.BX == prm.BXs;
+    const CUtensorMap* tm = x == 0 ? (small ? &tq_s : &tq_l) : x == 1 ? (small ? &tk_s : &tk_l) : (small ? &tv_s : &tv_l);
+    const uint32_t slot = pos % C::NSLOT;
+    const uint32_t bar = bar_full + 8u * slot;
+    fence_proxy_async();                                   // generic reads of the slot precede this async write
+    mbar_arrive_expect_tx(bar, (uint32_t)(gi.BX * RG * C::CH * 2));
+    tma_load_5d(sbase + C::OFF_ST + slot * C::SLOT_BYTES, tm, bar, gi.x0 - gi.shift, gi.y0, gi.z0, cs * C::CH, gi.b);
+  };
+  if (tid == 0)
+    for (uint32_t p = 0; p < (uint32_t)C::NSLOT; ++p) issue_box(p);
+
+  // ---- roles
+  const int ti = tid >> 7, row = tid & 127;                 // softmax / output: thread == row `row` of tile `ti`
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t tS = tmem_base + lane_addr + ti * 128, tO = tS + 64;
+  const int wi = row / WD, slot_in_win = row - wi * WD;
+  const int c_lo = wi * WD, c_hi = c_lo + WD;               // columns of this row's own window
+  const int rp_j = tid & 15, rp_c = (tid >> 4) & 7;         // repack: 16-byte chunk rp_j of channels rp_c, rp_c + 8 of tile ti
+  constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);
+  constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);
+  const float2 scale2 = make_float2(prm.scale_log2, prm.scale_log2);
+
+  uint32_t it = 0;
+  for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x, ++it) {
+    const GroupInfo gi = decode_group(prm, grp);
+    const uint32_t pitch = (uint32_t)(RG * gi.BX * 2);      // channel pitch of a staged box
+    // per-group repack recipe of this thread: byte offsets of its 8 source tokens inside one channel of a box
+    uint32_t off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t e = rowtab[rp_j * 8 + i];
+      const int col = (int)(e & 0xffffu) + ti * prm.G * W;  // column inside the group's x-range
+      const bool ok = e != 0xffffffffu && col < gi.nvalid * W;
+      off[i] = ok ? (uint32_t)(((int)(e >> 16) * gi.BX + gi.shift + col) * 2) : 0xffffffffu;
+    }
+    if (tid < RG) {                                         // global token offset of every (y, z) row of the group
+      const int kz = tid / W, ky = tid - kz * W;
+      const int y = gi.y0 + (g.nd >= 2 ? ky : 0), z = gi.z0 + (g.nd >= 3 ? kz : 0);
+      rowoff[tid] = (y >= 0 && y < g.s[1] && z >= 0 && z < g.s[2]) ? (z * g.s[1] + y) * g.s[0] : -1;
+    }
+
+    auto repack = [&](uint32_t pos, uint32_t tile_base, int cs) {
+      const uint32_t slot = pos % C::NSLOT;
+      mbar_wait(bar_full + 8u * slot, (pos / C::NSLOT) & 1u);
+      const uint32_t stg = sbase + C::OFF_ST + slot * C::SLOT_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = rp_c + 8 * h, c = cs * C::CH + cc;
+        const uint32_t src = stg + (uint32_t)cc * pitch;
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = off[i] != 0xffffffffu ? lds_u16(src + off[i]) : 0u;
+        const uint32_t dst = tile_base + (uint32_t)(ti * C::TILE_BYTES + (rp_j >> 3) * C::BOX_BYTES + c * 128 + (((rp_j & 7) ^ (c & 7)) << 4));
+        sts_v4(dst, v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+      }
+    };
+    auto release = [&](uint32_t pos) {                      // every thread has read the slot of box `pos`: refill it
+      __syncthreads();
+      if (tid == 0) issue_box(pos + C::NSLOT);
+    };
+
+    const uint32_t pos0 = it * C::BOXES;
+    // ---- Q / K slices: repack, then one K = 16 step of S = Q K^T per tile
+#pragma unroll 1
+    for (int cs = 0; cs < C::NCS; ++cs) {
+      repack(pos0 + 2 * cs, sbase + C::OFF_TQ, cs);
+      repack(pos0 + 2 * cs + 1, sbase + C::OFF_TK, cs);
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) { issue_box(pos0 + 2 * cs + C::NSLOT); issue_box(pos0 + 2 * cs + 1 + C::NSLOT); }
+      if (warp == 0) {
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int t = 0; t < C::NT; ++t) {
+            const uint64_t qdesc = make_smem_desc_sw128(sbase + C::OFF_TQ + t * C::TILE_BYTES, C::BOX_BYTES, 1024);
+            const uint64_t kdesc = make_smem_desc_sw128(sbase + C::OFF_TK + t * C::TILE_BYTES, C::BOX_BYTES, 1024);
+            mma_ss(tmem_base + t * 128, qdesc + (uint64_t)(cs * 128), kdesc + (uint64_t)(cs * 128), idesc_qk, cs > 0 ? 1u : 0u);
+          }
+          if (cs == C::NCS - 1) tc_commit(bar_s);
+        }
+        __syncwarp();
+      }
+    }
+    mbar_wait(bar_s, it & 1u);                              // S complete: the Q and K tiles are dead
+    tc_fence_after();
+    // ---- V slices into the Q tiles
+#pragma unroll 1
+    for (int cs = 0; cs < C::NCS; ++cs) {
+      repack(pos0 + 2 * C::NCS + cs, sbase + C::OFF_TQ, cs);
+      if (cs == C::NCS - 1) fence_proxy_async();
+      release(pos0 + 2 * C::NCS + cs);
+    }
+
+    // ---- softmax over the columns of this row's window (block-diagonal mask), as in fa_tc_win.cu
+    const long long gw = gi.gw0 + (long long)ti * prm.G + wi;
+    const bool valid = wi < prm.G && ti * prm.G + wi < gi.nvalid;
+    const int r_lo = valid ? c_lo : 0, r_hi = valid ? c_hi : 128;
+    uint32_t cls = 0;                                       // 2 bits per 32-column chunk: 1 = inside, 2 = outside, 0 = mixed
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const bool in = r_lo <= 32 * ch && 32 * ch + 32 <= r_hi, out = r_hi <= 32 * ch || r_lo >= 32 * ch + 32;
+      cls |= (__all_sync(0xffffffffu, in) ? 1u : (__all_sync(0xffffffffu, out) ? 2u : 0u)) << (2 * ch);
+    }
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      const uint32_t k = (cls >> (2 * ch)) & 3u;
+      if (k == 2u) continue;
+      uint32_t s[32];
+      tmem_ld32(tS + 32 * ch, s);
+      tmem_wait_ld();
+      if (k == 1u) {
+        float m0 = mx, m1 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(s[e]), __uint_as_float(s[e + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])));
+        }
+        mx = fmaxf(m0, m1);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int col = 32 * ch + e;
+          if (col >= r_lo && col < r_hi) mx = fmaxf(mx, __uint_as_float(s[e]));
+        }
+      }
+    }
+    const float m2 = valid ? mx * prm.scale_log2 : INFINITY;
+    const float2 negm2 = make_float2(-m2, -m2);
+    float2 ls2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      const uint32_t k = (cls >> (2 * ch)) & 3u;
+      uint32_t pk[16];
+      if (k == 2u) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      } else {
+        uint32_t s[32];
+        tmem_ld32(tS + 32 * ch, s);
+        tmem_wait_ld();
+        if (k == 1u) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, negm2);
+            const float2 p = make_float2(ex2(x.x), ex2(x.y));
+            ls2 = __fadd2_rn(ls2, p);
+            pk[e >> 1] = pack16<FMT>(p.x, p.y);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int col = 32 * ch + e;
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), scale2, negm2);
+            const float p0 = (col >= r_lo && col < r_hi) ? ex2(x.x) : 0.f;
+            const float p1 = (col + 1 >= r_lo && col + 1 < r_hi) ? ex2(x.y) : 0.f;
+            ls2 = __fadd2_rn(ls2, make_float2(p0, p1));
+            pk[e >> 1] = pack16<FMT>(p0, p1);
+          }
+        }
+      }
+      tmem_st16(tS + 16 * ch, pk);                          // P (16-bit) over the S columns already consumed
+    }
+    const float lsum = ls2.x + ls2.y;
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- O = P V per tile (A = P from TMEM, B = V K-major in the Q tiles, K = 128 keys)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < C::NT; ++t) {
+          const uint64_t vdesc = make_smem_desc_sw128(sbase + C::OFF_TQ + t * C::TILE_BYTES, 16, 1024);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            mma_ts(tmem_base + t * 128 + 64, tmem_base + t * 128 + ks * 8,
+                   vdesc + (uint64_t)((ks >> 2) * (C::BOX_BYTES >> 4) + (ks & 3) * 2), idesc_pv, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_o);
+      }
+      __syncwarp();
+    }
+    if (valid) {                                            // l, m for every slot, padded ones included
+      prm.l[gw * WD + slot_in_win] = lsum;
+      prm.m[gw * WD + slot_in_win] = m2 * LN2;
+    }
+    const float inv_l = valid ? 1.f / lsum : 0.f;
+    mbar_wait(bar_o, it & 1u);
+    tc_fence_after();
+
+    // ---- O rows -> 16-bit output staging [channel][(y, z) row][x across the group] over the dead K tiles
+    const uint32_t ostg = sbase + C::OFF_TK;
+    const uint32_t cpitch = (uint32_t)(RG * TW * 2);
+    if (valid) {
+      const uint32_t e = rowtab[row];
+      const uint32_t o0 = ostg + (uint32_t)(((int)(e >> 16) * TW + ti * prm.G * W + (int)(e & 0xffffu)) * 2);
+#pragma unroll 1
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + 32 * ch, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e2 = 0; e2 < 32; ++e2) sts_u16(o0 + (uint32_t)(32 * ch + e2) * cpitch, cvt16<FMT>(__uint_as_float(o[e2]) * inv_l));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- write the runs: (channel, row) run = the group's TW tokens of one line; piece = 2 tokens aligned to an even
+    //      global element index (4-byte store), clipped to the volume and to the windows that exist
+    {
+      const int xa = gi.x0 < 0 ? 0 : gi.x0;
+      const int xe_ = gi.x0 + gi.nvalid * W;
+      const int xe = xe_ > g.s[0] ? g.s[0] : xe_;
+      const int npieces = D * RG * prm.NP;
+      T* ybase = static_cast<T*>(prm.y) + (long long)gi.b * D * N;
+      for (int idx = tid; idx < npieces; idx += C::THREADS) {
+        const int run = (int)__umulhi((unsigned)idx, prm.magicNP), p = idx - run * prm.NP;
+        const int c = run / RG, rowidx = run - c * RG;
+        const int ro = rowoff[rowidx];
+        if (ro < 0) continue;
+        const long long e0 = (long long)c * N + ro;         // element offset of x = 0 of this line inside the batch element
+        const int par = (int)((e0 + gi.x0) & 1);            // pairs start at even global element indices
+        const int t0 = gi.x0 + 2 * p - par;                 // x of the pair's first token
+        const bool h0 = t0 >= xa && t0 < xe, h1 = t0 + 1 >= xa && t0 + 1 < xe;
+        if (!h0 && !h1) continue;
+        const uint32_t sa = ostg + (uint32_t)c * cpitch + (uint32_t)((rowidx * TW + (t0 - gi.x0)) * 2);
+        if (h0 && h1) {
+          const uint32_t v = lds_u16(sa) | (lds_u16(sa + 2) << 16);
+          *reinterpret_cast<uint32_t*>(ybase + e0 + t0) = v;
+        } else if (h0) {
+          *reinterpret_cast<unsigned short*>(ybase + e0 + t0) = (unsigned short)lds_u16(sa);
+        } else {
+          *reinterpret_cast<unsigned short*>(ybase + e0 + t0 + 1) = (unsigned short)lds_u16(sa + 2);
+        }
+      }
+    }
+    __syncthreads();      // output staging (= K tiles), row table and TMEM are free for the next group
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int FMT>
+int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
+  using C = XCfg;
+  const int dtype = FMT ? FA_BF16 : FA_F16;
+  CUtensorMap tm[6];
+  memset(tm, 0, sizeof(tm));
+  const void* src[3] = {a.q, a.k, a.v};
+  const int by = g.nd >= 2 ? g.W : 1, bz = g.nd >= 3 ? g.W : 1;
+  for (int x = 0; x < 3; ++x) {
+    int rc;
+    if ((rc = make_win_tmap_box(&tm[x], src[x], dtype, g, C::D, prm.BXs, by, bz, C::CH))) return rc;
+    if ((rc = make_win_tmap_box(&tm[3 + x], src[x], dtype, g, C::D, prm.BXl, by, bz, C::CH))) return rc;
+  }
+  auto kern = tc_winx_fwd_kernel<FMT>;
+  FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(prm.ngroups < sms ? prm.ngroups : sms);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
+}  // namespace
+
+// Does the streamed kernel take this call?  Exact-cover windows (stride == W), d = dv = 64, 16-bit, TMA-legal rows
+// (x extent a multiple of 8 tokens, 16-byte aligned bases), no fold accumulator, boxes that fit a staging slot.
+bool tc_winx_supported(const Geo& g, const FwdArgs& a, int dtype) {
+  using C = XCfg;
+  if (dtype != FA_BF16 && dtype != FA_F16) return false;
+  if (g.mode != MODE_WINDOWED || g.d != 64 || g.dv != 64 || a.acc) return false;
+  if (g.stride != g.W || g.s[0] % 8 != 0 || g.WD > 128 || g.WD < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return false;
+  if (reinterpret_cast<uintptr_t>(a.o) & 3) return false;
+  if ((g.N & 1) || g.B > 0x7fffffffLL || g.padv[0] > 1000) return false;
+  const int G = 128 / g.WD, nwc = C::NT * G, TW = nwc * g.W, RG = g.WD / g.W;
+  const int BXl = (TW + 7 + 7) / 8 * 8;
+  if (RG > 64 || TW > 0x7fff || (long long)BXl * RG * C::CH * 2 > C::SLOT_BYTES) return false;
+  if ((long long)C::D * RG * TW * 2 > (long long)C::NT * C::TILE_BYTES) return false;
+  if ((long long)C::D * RG * (TW / 2 + 1) * (TW / 2 + 1) >= 0xffffffffLL) return false;    // exact magic division of the piece index
+  return true;
+}
+
+int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
+  using C = XCfg;
+  if (!tc_winx_supported(g, a, dtype)) { set_error("tc_winx_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
+  XParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.q = a.q; prm.k = a.k; prm.v = a.v; prm.y = a.o; prm.l = a.l; prm.m = a.m;
+  prm.g = g;
+  prm.G = 128 / g.WD; prm.nwc = C::NT * prm.G; prm.TW = prm.nwc * g.W; prm.RG = g.WD / g.W;
+  prm.gpr = (g.o[0] + prm.nwc - 1) / prm.nwc;
+  prm.BXs = (prm.TW + 7) / 8 * 8;
+  prm.BXl = (prm.TW + 7 + 7) / 8 * 8;
+  prm.NP = prm.TW / 2 + 1;
+  prm.magicNP = (unsigned)((0x100000000ULL + prm.NP - 1) / prm.NP);
+  prm.ngroups = (long long)prm.gpr * g.o[1] * g.o[2] * g.B;
+  prm.scale_log2 = g.tau * LOG2E;
+  return dtype == FA_BF16 ? launch_winx<1>(g, a, prm, st) : launch_winx<0>(g, a, prm, st);
+}
+
+}  // namespace fa
