@@ -1080,8 +1080,10 @@ int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
 int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   if (!tc_win_supported(g, dtype)) { set_error("tc_win_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
   const int fmt = dtype == FA_BF16 ? 1 : 0;
-  // large exact-cover problems: the streamed kernel of fa_tc_winx.cu (TMA boxes + 16-byte repack, four tiles per SM).
-  // FA_WINX = 0 never, 1 whenever it applies, unset: when every SM gets at least four of its groups
+  // large exact-cover 3-D problems: the streamed kernel of fa_tc_winx.cu (TMA boxes + 16-byte repack, four tiles per SM).
+  // Measured on B200 (profiles/r2f_winx.md): config 5 at B = 64 6.45 vs 7.33 ms, one 256^3 volume 4.6 vs 9.8 ms; 2-D
+  // images (short (y) columns: 7 rows per box) are faster on the per-thread gather below (0.75 vs 1.35 ms at B = 512).
+  // FA_WINX = 0 never, 1 whenever it applies, unset: 3-D volumes with at least four groups per SM
   {
     static const int winx = [] { const char* e = getenv("FA_WINX"); return e ? atoi(e) : -1; }();
     if (winx != 0 && tc_winx_supported(g, a, dtype)) {
@@ -1090,7 +1092,7 @@ int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       const int nwc = 4 * (128 / g.WD);
       const long long groups = (long long)((g.o[0] + nwc - 1) / nwc) * g.o[1] * g.o[2] * g.B;
-      if (winx == 1 || groups >= 4LL * sms) return tc_winx_fwd(g, a, dtype, st);
+      if (winx == 1 || (g.nd == 3 && groups >= 4LL * sms)) return tc_winx_fwd(g, a, dtype, st);
     }
   }
   if (g.d == 128) return fmt ? launch_win_fwd<128, 1, 1>(g, a, st) : launch_win_fwd<128, 1, 0>(g, a, st);

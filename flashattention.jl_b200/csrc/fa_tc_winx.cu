@@ -62,10 +62,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_5d(const void* tmap, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 struct XCfg {
   static constexpr int D = 64;
   static constexpr int NT = 4;                               // 128-row tiles per CTA = all 512 TMEM columns
-  static constexpr int THREADS = 128 * NT;
+  static constexpr int CONSUMERS = 128 * NT;                 // warps 0..15: repack / softmax / output (thread == tile row)
+  static constexpr int THREADS = CONSUMERS + 32;             // warp 16: TMA producer
   static constexpr int CH = 16;                              // channels per TMA box = one tcgen05.mma K step
   static constexpr int NCS = D / CH;
   static constexpr int BOXES = 3 * NCS;                      // boxes per group: Q0 K0 .. Q3 K3 V0 .. V3
@@ -91,11 +97,20 @@ struct XParams {
   int G, nwc, TW, RG;          // windows per tile / per group, tokens per (y, z) row of a group, rows per window
   int gpr;                     // groups per window row
   int BXs, BXl;                // box extents along x (tokens): small when shift + TW fits, large otherwise
-  int NP;                      // 4-byte store pieces per output run
-  unsigned magicNP;            // ceil(2^32 / NP)
+  int NP, TWP;                 // output: 4-byte pairs per run (TW / 2 + 1), tokens per staged row (2 * NP)
+  unsigned magicNP;            // ceil(2^32 / NP): exact i / NP for i < RG * NP
   long long ngroups;
   float scale_log2;
+  int l2_prefetch;             // producer prefetches the next group's boxes into L2 (FA_WINX_PF=0 disables)
+  int dbg;                     // FA_TRACE builds: FA_WINX_DBG experiment switch (0 = product behaviour)
+  long long* trace;            // FA_TRACE builds: CTA 1 records clock64() per phase of its first 16 groups (20 events each)
 };
+
+#ifdef FA_TRACE
+#define XTRACE(ev) do { if (prm.trace && blockIdx.x == 1 && tid == 0 && it < 16) prm.trace[it * 20 + (ev)] = clock64(); } while (0)
+#else
+#define XTRACE(ev) do {} while (0)
+#endif
 
 struct GroupInfo {
   long long gw0;               // linear index (batch included) of the group's first window
@@ -104,17 +119,18 @@ struct GroupInfo {
   int shift, BX;               // x0 - box start (0..7), box extent used
 };
 
-__device__ __forceinline__ GroupInfo decode_group(const XParams& prm, long long grp) {
+__device__ __forceinline__ GroupInfo decode_group(const XParams& prm, unsigned grp) {   // ngroups < 2^31: 32-bit divisions
   const Geo& g = prm.g;
   GroupInfo gi;
-  const long long rowi = grp / prm.gpr;
-  const int gix = (int)(grp - rowi * prm.gpr);
+  const unsigned rowi = grp / (unsigned)prm.gpr;
+  const int gix = (int)(grp - rowi * (unsigned)prm.gpr);
   const int wx0 = gix * prm.nwc;
   gi.nvalid = g.o[0] - wx0 < prm.nwc ? g.o[0] - wx0 : prm.nwc;
-  const int wy = (int)(rowi % g.o[1]);
-  const long long r2 = rowi / g.o[1];
-  const int wz = (int)(r2 % g.o[2]);
-  gi.b = (int)(r2 / g.o[2]);
+  const unsigned r2 = rowi / (unsigned)g.o[1];
+  const int wy = (int)(rowi - r2 * (unsigned)g.o[1]);
+  const unsigned r3 = r2 / (unsigned)g.o[2];
+  const int wz = (int)(r2 - r3 * (unsigned)g.o[2]);
+  gi.b = (int)r3;
   gi.gw0 = (((long long)gi.b * g.o[2] + wz) * g.o[1] + wy) * g.o[0] + wx0;
   gi.x0 = wx0 * g.stride - g.padv[0];
   gi.y0 = g.nd >= 2 ? wy * g.stride - g.padv[1] : 0;
@@ -138,15 +154,16 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
   const uint32_t sbase = smem_u32(sptr);
   uint32_t* rowtab = reinterpret_cast<uint32_t*>(sptr + C::OFF_ROWTAB);
   int* rowoff = reinterpret_cast<int*>(sptr + C::OFF_ROWOFF);
-  const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16, bar_full = bar_s + 32;   // bar_full[NSLOT]
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_s = sbase + C::OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16;
+  const uint32_t bar_full = bar_s + 32, bar_empty = bar_s + 64;      // [NSLOT] each: box landed / every consumer warp has read it
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Geo& g = prm.g;
   const long long N = g.N;
   const int W = g.W, WD = g.WD, RG = prm.RG, TW = prm.TW;
 
   if (tid == 0) {
     mbar_init(bar_s, 1); mbar_init(bar_o, 1);
-    for (int i = 0; i < C::NSLOT; ++i) mbar_init(bar_full + 8 * i, 1);
+    for (int i = 0; i < C::NSLOT; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, C::CONSUMERS / 32); }
     fence_barrier_init();
     prefetch_tensormap(&tq_s); prefetch_tensormap(&tk_s); prefetch_tensormap(&tv_s);
     prefetch_tensormap(&tq_l); prefetch_tensormap(&tk_l); prefetch_tensormap(&tv_l);
@@ -169,23 +186,45 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // ---- the TMA stream: box number `pos` of this CTA = box (pos % BOXES) of its (pos / BOXES)-th group -> slot pos % NSLOT
-  auto issue_box = [&](uint32_t pos) {
-    const long long grp = (long long)blockIdx.x + (long long)(pos / C::BOXES) * gridDim.x;
-    if (grp >= prm.ngroups) return;
-    const int j = (int)(pos % C::BOXES);
-    const int x = j < 2 * C::NCS ? (j & 1) : 2, cs = j < 2 * C::NCS ? (j >> 1) : j - 2 * C::NCS;
-    const GroupInfo gi = decode_group(prm, grp);
-    const bool small = gi.BX == prm.BXs;
-    const CUtensorMap* tm = x == 0 ? (small ? &tq_s : &tq_l) : x == 1 ? (small ? &tk_s : &tk_l) : (small ? &tv_s : &tv_l);
-    const uint32_t slot = pos % C::NSLOT;
-    const uint32_t bar = bar_full + 8u * slot;
-    fence_proxy_async();                                   // generic reads of the slot precede this async write
-    mbar_arrive_expect_tx(bar, (uint32_t)(gi.BX * RG * C::CH * 2));
-    tma_load_5d(sbase + C::OFF_ST + slot * C::SLOT_BYTES, tm, bar, gi.x0 - gi.shift, gi.y0, gi.z0, cs * C::CH, gi.b);
-  };
-  if (tid == 0)
-    for (uint32_t p = 0; p < (uint32_t)C::NSLOT; ++p) issue_box(p);
+  // ---- warp 16: the TMA stream.  Box number `pos` of this CTA = box (pos % BOXES) of its (pos / BOXES)-th group, into
+  //      slot pos % NSLOT as soon as every consumer warp has released that slot's previous box.
+  if (warp == C::CONSUMERS / 32) {
+    if (lane == 0) {
+      uint32_t pos = 0;
+      for (unsigned grp = blockIdx.x; grp < (unsigned)prm.ngroups; grp += gridDim.x) {
+        const GroupInfo gi = decode_group(prm, grp);
+        const bool small = gi.BX == prm.BXs;
+        const uint32_t bytes = (uint32_t)(gi.BX * RG * C::CH * 2);
+        // The stream can only run NSLOT boxes (77 KB) ahead, which at DRAM latency is ~30 B/clk: pull the NEXT group's
+        // boxes into L2 now, a whole group time ahead, so that its loads are L2 hits.
+        if (grp + gridDim.x < (unsigned)prm.ngroups && prm.l2_prefetch) {
+          const GroupInfo gn = decode_group(prm, grp + gridDim.x);
+          const bool sm2 = gn.BX == prm.BXs;
+#pragma unroll 1
+          for (int j = 0; j < C::BOXES; ++j) {
+            const int x = j < 2 * C::NCS ? (j & 1) : 2, cs = j < 2 * C::NCS ? (j >> 1) : j - 2 * C::NCS;
+            const CUtensorMap* tm = x == 0 ? (sm2 ? &tq_s : &tq_l) : x == 1 ? (sm2 ? &tk_s : &tk_l) : (sm2 ? &tv_s : &tv_l);
+            tma_prefetch_5d(tm, gn.x0 - gn.shift, gn.y0, gn.z0, cs * C::CH, gn.b);
+          }
+        }
+#pragma unroll 1
+        for (int j = 0; j < C::BOXES; ++j, ++pos) {
+          const int x = j < 2 * C::NCS ? (j & 1) : 2, cs = j < 2 * C::NCS ? (j >> 1) : j - 2 * C::NCS;
+          const CUtensorMap* tm = x == 0 ? (small ? &tq_s : &tq_l) : x == 1 ? (small ? &tk_s : &tk_l) : (small ? &tv_s : &tv_l);
+          const uint32_t slot = pos % C::NSLOT, fill = pos / C::NSLOT;
+          if (fill > 0) mbar_wait(bar_empty + 8u * slot, (fill - 1) & 1u);
+          fence_proxy_async();                             // the consumers' generic reads of the slot precede this async write
+          mbar_arrive_expect_tx(bar_full + 8u * slot, bytes);
+          tma_load_5d(sbase + C::OFF_ST + slot * C::SLOT_BYTES, tm, bar_full + 8u * slot, gi.x0 - gi.shift, gi.y0, gi.z0, cs * C::CH, gi.b);
+        }
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();                                       // matches the barrier in front of the TMEM deallocation
+    return;
+  }
+  auto csync = [] { asm volatile("bar.sync 1, %0;" ::"n"(C::CONSUMERS) : "memory"); };    // barrier of the 16 consumer warps
 
   // ---- roles
   const int ti = tid >> 7, row = tid & 127;                 // softmax / output: thread == row `row` of tile `ti`
@@ -193,13 +232,19 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
   const uint32_t tS = tmem_base + lane_addr + ti * 128, tO = tS + 64;
   const int wi = row / WD, slot_in_win = row - wi * WD;
   const int c_lo = wi * WD, c_hi = c_lo + WD;               // columns of this row's own window
-  const int rp_j = tid & 15, rp_c = (tid >> 4) & 7;         // repack: 16-byte chunk rp_j of channels rp_c, rp_c + 8 of tile ti
+  // repack: this thread produces the 16-byte chunk rp_j (tile rows 8 rp_j .. 8 rp_j + 7) of channels rp_c and rp_c + 8
+  // of tile rp_t.  Lane bits = (c0, c1, j2, t0, t1): the 8 lanes of a quarter warp store to 8 different 16-byte bank
+  // groups ((j ^ c) & 7 distinct) and the 32 two-byte loads of a warp spread over the four windows of the group --
+  // 2.2 wavefronts per load instead of 6.5 with lanes along j (64-byte staging rows alias to two bank groups).
+  const int rp_t = (lane >> 3) & 3;
+  const int rp_j = (warp & 3) | (((lane >> 2) & 1) << 2) | (((warp >> 2) & 1) << 3);
+  const int rp_c = (lane & 3) | (((warp >> 3) & 1) << 2);
   constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);
   constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);
   const float2 scale2 = make_float2(prm.scale_log2, prm.scale_log2);
 
   uint32_t it = 0;
-  for (long long grp = blockIdx.x; grp < prm.ngroups; grp += gridDim.x, ++it) {
+  for (unsigned grp = blockIdx.x; grp < (unsigned)prm.ngroups; grp += gridDim.x, ++it) {
     const GroupInfo gi = decode_group(prm, grp);
     const uint32_t pitch = (uint32_t)(RG * gi.BX * 2);      // channel pitch of a staged box
     // per-group repack recipe of this thread: byte offsets of its 8 source tokens inside one channel of a box
@@ -207,7 +252,7 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint32_t e = rowtab[rp_j * 8 + i];
-      const int col = (int)(e & 0xffffu) + ti * prm.G * W;  // column inside the group's x-range
+      const int col = (int)(e & 0xffffu) + rp_t * prm.G * W;  // column inside the group's x-range
       const bool ok = e != 0xffffffffu && col < gi.nvalid * W;
       off[i] = ok ? (uint32_t)(((int)(e >> 16) * gi.BX + gi.shift + col) * 2) : 0xffffffffu;
     }
@@ -221,6 +266,9 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
       const uint32_t slot = pos % C::NSLOT;
       mbar_wait(bar_full + 8u * slot, (pos / C::NSLOT) & 1u);
       const uint32_t stg = sbase + C::OFF_ST + slot * C::SLOT_BYTES;
+#ifdef FA_TRACE
+      if (prm.dbg == 4) { __syncwarp(); if (lane == 0) mbar_arrive(bar_empty + 8u * slot); return; }   // TMA stream alone
+#endif
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int cc = rp_c + 8 * h, c = cs * C::CH + cc;
@@ -228,24 +276,23 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
         uint32_t v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = off[i] != 0xffffffffu ? lds_u16(src + off[i]) : 0u;
-        const uint32_t dst = tile_base + (uint32_t)(ti * C::TILE_BYTES + (rp_j >> 3) * C::BOX_BYTES + c * 128 + (((rp_j & 7) ^ (c & 7)) << 4));
+        const uint32_t dst = tile_base + (uint32_t)(rp_t * C::TILE_BYTES + (rp_j >> 3) * C::BOX_BYTES + c * 128 + (((rp_j & 7) ^ (c & 7)) << 4));
         sts_v4(dst, v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
       }
-    };
-    auto release = [&](uint32_t pos) {                      // every thread has read the slot of box `pos`: refill it
-      __syncthreads();
-      if (tid == 0) issue_box(pos + C::NSLOT);
+      __syncwarp();                                         // the warp's loads of the slot have completed (their values were stored)
+      if (lane == 0) mbar_arrive(bar_empty + 8u * slot);
     };
 
     const uint32_t pos0 = it * C::BOXES;
+    XTRACE(0);                                              // group start (recipe built)
     // ---- Q / K slices: repack, then one K = 16 step of S = Q K^T per tile
 #pragma unroll 1
     for (int cs = 0; cs < C::NCS; ++cs) {
       repack(pos0 + 2 * cs, sbase + C::OFF_TQ, cs);
       repack(pos0 + 2 * cs + 1, sbase + C::OFF_TK, cs);
       fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) { issue_box(pos0 + 2 * cs + C::NSLOT); issue_box(pos0 + 2 * cs + 1 + C::NSLOT); }
+      csync();
+      XTRACE(1 + cs);                                       // Q/K slice cs repacked
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
@@ -262,13 +309,14 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
     }
     mbar_wait(bar_s, it & 1u);                              // S complete: the Q and K tiles are dead
     tc_fence_after();
+    XTRACE(5);                                              // S complete
     // ---- V slices into the Q tiles
 #pragma unroll 1
     for (int cs = 0; cs < C::NCS; ++cs) {
       repack(pos0 + 2 * C::NCS + cs, sbase + C::OFF_TQ, cs);
-      if (cs == C::NCS - 1) fence_proxy_async();
-      release(pos0 + 2 * C::NCS + cs);
+      XTRACE(6 + cs);                                       // V slice cs repacked
     }
+    fence_proxy_async();
 
     // ---- softmax over the columns of this row's window (block-diagonal mask), as in fa_tc_win.cu
     const long long gw = gi.gw0 + (long long)ti * prm.G + wi;
@@ -343,7 +391,8 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
     const float lsum = ls2.x + ls2.y;
     tmem_wait_st();
     tc_fence_before();
-    __syncthreads();
+    csync();
+    XTRACE(10);                                             // softmax done (all warps)
 
     // ---- O = P V per tile (A = P from TMEM, B = V K-major in the Q tiles, K = 128 keys)
     if (warp == 0) {
@@ -368,59 +417,82 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
     const float inv_l = valid ? 1.f / lsum : 0.f;
     mbar_wait(bar_o, it & 1u);
     tc_fence_after();
+    XTRACE(11);                                             // O ready
 
-    // ---- O rows -> 16-bit output staging [channel][(y, z) row][x across the group] over the dead K tiles
-    const uint32_t ostg = sbase + C::OFF_TK;
-    const uint32_t cpitch = (uint32_t)(RG * TW * 2);
-    if (valid) {
-      const uint32_t e = rowtab[row];
-      const uint32_t o0 = ostg + (uint32_t)(((int)(e >> 16) * TW + ti * prm.G * W + (int)(e & 0xffffu)) * 2);
+    // ---- O rows -> 16-bit output staging [channel][(y, z) row][x across the group] over the dead V and K tiles.  Token x
+    //      of a row sits at index x - x0 + par (par = x0 & 1; rows start at even global element indices because the x
+    //      extent is even), so that a pair of tokens at an even global index is one aligned 32-bit word here.
+    const uint32_t ostg = sbase + C::OFF_TQ;
+    const int par = gi.x0 & 1;
+    const uint32_t cpitch = (uint32_t)(RG * prm.TWP * 2);
+    {
+      // (tcgen05.ld is warp-collective: every thread reads its row, only rows of existing windows are stored)
+      const uint32_t e = valid ? rowtab[row] : 0u;
+      const uint32_t o0 = ostg + (uint32_t)(((int)(e >> 16) * prm.TWP + ti * prm.G * W + (int)(e & 0xffffu) + par) * 2);
 #pragma unroll 1
       for (int ch = 0; ch < D / 32; ++ch) {
         uint32_t o[32];
         tmem_ld32(tO + 32 * ch, o);
         tmem_wait_ld();
+        if (valid) {
 #pragma unroll
-        for (int e2 = 0; e2 < 32; ++e2) sts_u16(o0 + (uint32_t)(32 * ch + e2) * cpitch, cvt16<FMT>(__uint_as_float(o[e2]) * inv_l));
+          for (int e2 = 0; e2 < 32; ++e2) sts_u16(o0 + (uint32_t)(32 * ch + e2) * cpitch, cvt16<FMT>(__uint_as_float(o[e2]) * inv_l));
+        }
       }
     }
     tc_fence_before();
-    __syncthreads();
+    csync();
+    XTRACE(12);                                             // O staged
 
-    // ---- write the runs: (channel, row) run = the group's TW tokens of one line; piece = 2 tokens aligned to an even
-    //      global element index (4-byte store), clipped to the volume and to the windows that exist
+    // ---- write the runs: item = (row, pair) of one channel, pair = 2 tokens at an even global element index = one
+    //      32-bit shared load + one 4-byte store (2-byte stores at the clipped ends of a run).  Lanes run along the pairs
+    //      of a row, then the rows; warp w writes the channels w, w + 16, w + 32, w + 48.
     {
       const int xa = gi.x0 < 0 ? 0 : gi.x0;
       const int xe_ = gi.x0 + gi.nvalid * W;
       const int xe = xe_ > g.s[0] ? g.s[0] : xe_;
-      const int npieces = D * RG * prm.NP;
-      T* ybase = static_cast<T*>(prm.y) + (long long)gi.b * D * N;
-      for (int idx = tid; idx < npieces; idx += C::THREADS) {
-        const int run = (int)__umulhi((unsigned)idx, prm.magicNP), p = idx - run * prm.NP;
-        const int c = run / RG, rowidx = run - c * RG;
+      T* ybase = static_cast<T*>(prm.y) + ((long long)gi.b * D + warp) * N;
+      const uint32_t sw = ostg + (uint32_t)warp * cpitch;
+      const long long cstep = (long long)(C::CONSUMERS / 32) * N;
+      const uint32_t sstep = (uint32_t)(C::CONSUMERS / 32) * cpitch;
+      int nitems = RG * prm.NP;
+#ifdef FA_TRACE
+      if (prm.dbg == 3) nitems = 0;                         // experiment: no output loop at all
+#endif
+      for (int i = lane; i < nitems; i += 32) {
+        const int rowidx = (int)__umulhi((unsigned)i, prm.magicNP), p = i - rowidx * prm.NP;
         const int ro = rowoff[rowidx];
-        if (ro < 0) continue;
-        const long long e0 = (long long)c * N + ro;         // element offset of x = 0 of this line inside the batch element
-        const int par = (int)((e0 + gi.x0) & 1);            // pairs start at even global element indices
-        const int t0 = gi.x0 + 2 * p - par;                 // x of the pair's first token
+        const int t0 = gi.x0 - par + 2 * p;                 // x of the pair's first token
         const bool h0 = t0 >= xa && t0 < xe, h1 = t0 + 1 >= xa && t0 + 1 < xe;
-        if (!h0 && !h1) continue;
-        const uint32_t sa = ostg + (uint32_t)c * cpitch + (uint32_t)((rowidx * TW + (t0 - gi.x0)) * 2);
+        if (ro < 0 || (!h0 && !h1)) continue;
+        uint32_t sa = sw + (uint32_t)((rowidx * prm.TWP + 2 * p) * 2);
+        T* yp = ybase + ro + t0;
         if (h0 && h1) {
-          const uint32_t v = lds_u16(sa) | (lds_u16(sa + 2) << 16);
-          *reinterpret_cast<uint32_t*>(ybase + e0 + t0) = v;
-        } else if (h0) {
-          *reinterpret_cast<unsigned short*>(ybase + e0 + t0) = (unsigned short)lds_u16(sa);
+#pragma unroll
+          for (int c4 = 0; c4 < D / (C::CONSUMERS / 32); ++c4, sa += sstep, yp += cstep) {
+            uint32_t v;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sa));
+#ifdef FA_TRACE
+            if (prm.dbg == 1 && v != 0x7fc12345u) continue;   // experiment: shared loads only
+            if (prm.dbg == 5) { yp = static_cast<T*>(prm.y) + (long long)(((blockIdx.x * 16 + warp) * 4 + c4) * 1024 + lane * 2); }   // experiment: dense, fully coalesced stores
+#endif
+            *reinterpret_cast<uint32_t*>(yp) = v;
+          }
         } else {
-          *reinterpret_cast<unsigned short*>(ybase + e0 + t0 + 1) = (unsigned short)lds_u16(sa + 2);
+          const uint32_t sa1 = sa + (h0 ? 0u : 2u);
+          T* yp1 = yp + (h0 ? 0 : 1);
+#pragma unroll
+          for (int c4 = 0; c4 < D / (C::CONSUMERS / 32); ++c4)
+            *reinterpret_cast<unsigned short*>(yp1 + c4 * cstep) = (unsigned short)lds_u16(sa1 + c4 * sstep);
         }
       }
     }
-    __syncthreads();      // output staging (= K tiles), row table and TMEM are free for the next group
+    csync();              // output staging (= K tiles), row table and TMEM are free for the next group
+    XTRACE(13);                                             // runs written
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                                         // all 17 warps (the producer arrives from its own branch)
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -459,12 +531,12 @@ bool tc_winx_supported(const Geo& g, const FwdArgs& a, int dtype) {
   if (g.stride != g.W || g.s[0] % 8 != 0 || g.WD > 128 || g.WD < 1) return false;
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return false;
   if (reinterpret_cast<uintptr_t>(a.o) & 3) return false;
-  if ((g.N & 1) || g.B > 0x7fffffffLL || g.padv[0] > 1000) return false;
+  if ((g.N & 1) || g.N * 64 > 0x7fffffffLL || g.padv[0] > 1000) return false;
+  if ((long long)((g.o[0] + 3) / 4 + 1) * g.o[1] * g.o[2] * g.B > 0x7fffffffLL) return false;      // 32-bit group index
   const int G = 128 / g.WD, nwc = C::NT * G, TW = nwc * g.W, RG = g.WD / g.W;
   const int BXl = (TW + 7 + 7) / 8 * 8;
-  if (RG > 64 || TW > 0x7fff || (long long)BXl * RG * C::CH * 2 > C::SLOT_BYTES) return false;
-  if ((long long)C::D * RG * TW * 2 > (long long)C::NT * C::TILE_BYTES) return false;
-  if ((long long)C::D * RG * (TW / 2 + 1) * (TW / 2 + 1) >= 0xffffffffLL) return false;    // exact magic division of the piece index
+  if (RG > 64 || BXl > 256 || (long long)BXl * RG * C::CH * 2 > C::SLOT_BYTES) return false;   // TMA box extents <= 256
+  if ((long long)C::D * RG * (TW + 2) * 2 > 2LL * C::NT * C::TILE_BYTES) return false;      // output staging over the V and K tiles
   return true;
 }
 
@@ -480,9 +552,17 @@ int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.BXs = (prm.TW + 7) / 8 * 8;
   prm.BXl = (prm.TW + 7 + 7) / 8 * 8;
   prm.NP = prm.TW / 2 + 1;
+  prm.TWP = 2 * prm.NP;
   prm.magicNP = (unsigned)((0x100000000ULL + prm.NP - 1) / prm.NP);
   prm.ngroups = (long long)prm.gpr * g.o[1] * g.o[2] * g.B;
   prm.scale_log2 = g.tau * LOG2E;
+  prm.trace = nullptr;
+  prm.dbg = 0;
+  { static const int pf = [] { const char* e = getenv("FA_WINX_PF"); return e ? atoi(e) : 1; }(); prm.l2_prefetch = pf; }
+#ifdef FA_TRACE
+  { const char* e = getenv("FA_WINX_DBG"); prm.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
+#endif
   return dtype == FA_BF16 ? launch_winx<1>(g, a, prm, st) : launch_winx<0>(g, a, prm, st);
 }
 

@@ -244,3 +244,42 @@ def test_host_call_rejects_bad_device_and_keeps_current_device():
     rc = fa.lib.fa_dense_fwd_host(p(x), p(x), p(x), p(O), p(l), p(m), 64, 16, 16, 1, 0, 0, 99)
     assert rc == 1 and b"out of range" in fa.lib.fa_last_error_string()
     assert torch.cuda.current_device() == before
+
+
+# ------------------------------------------------------------------------------- streamed windowed kernel (fa_tc_winx.cu)
+def test_windowed_streamed_kernel_forced():
+    """csrc/fa_tc_winx.cu forced on for small geometries (FA_WINX=1, read once per process -> subprocess): 2-D / 3-D
+    exact-cover windows, short last groups, all box shifts, default padding (NaN planes), bf16 and fp16, 2e-3 against
+    the oracle.  By default the kernel takes 3-D volumes with >= 4 groups per SM: the config-5 volume tests
+    (test_gpu_parity.py::test_windowed_config5_geometry_tc at B = 1 stays on the round-1 kernel; the B >= 4 case below)."""
+    import os, subprocess, sys
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "check_winx.py")
+    r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=900, env=dict(os.environ, FA_WINX="1"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_windowed_streamed_kernel_default_dispatch_config5_batch():
+    """config 5 at batch 4 (43904 windows = 10976 groups >= 4 per SM): the default dispatch takes the streamed kernel;
+    sampled windows against the oracle evaluated on those windows only (the full oracle at B = 4 is slow)."""
+    B = 4
+    q, k, v = (randn_np((64, 64, 64, 64, B), s, BF16) for s in range(3))
+    Q, K, V = (to_dev(t, BF16) for t in (q, k, v))
+    y, l, m = fa.windowed_fa(Q, K, V, 5, 5, 3)
+    assert fa.last_path() == "tc" and tuple(l.shape) == (125, 1, 2744, B)
+    yy = to_np(y)
+    rng = np.random.default_rng(3)
+    for _ in range(24):
+        wx, wy, wz, b = (int(rng.integers(0, 14)) for _ in range(3)) + (int(rng.integers(0, B)),)
+        lo = [5 * w - 3 for w in (wx, wy, wz)]
+        sl = tuple(slice(max(0, a), min(64, a + 5)) for a in lo)
+        qs, ks, vs = (np.asfortranarray(t[sl + (slice(None), slice(b, b + 1))].astype(np.float64)) for t in (q, k, v))
+        pad = [(max(0, -a), max(0, a + 5 - 64)) for a in lo] + [(0, 0), (0, 0)]
+        qs, ks, vs = (np.asfortranarray(np.pad(t, pad)) for t in (qs, ks, vs))           # the window with its zero padding
+        y0, l0, m0 = fo.dense_fa(qs, ks, vs)                                              # one window = dense attention on 125 slots
+        inner = tuple(slice(p_[0], 5 - p_[1]) for p_ in pad[:3])
+        assert rel_err(yy[sl + (slice(None), b)], y0[inner + (slice(None), 0)], BF16) < 2e-3
+        w_lin = (wz * 14 + wy) * 14 + wx
+        assert rel_err(to_np(l)[:, 0, w_lin, b], l0[:, 0, 0]) < 2e-3
+    ones = fa.jl_empty((64, 64, 64, 64, B), BF16).fill_(1)
+    y1, _, _ = fa.windowed_fa(Q, K, ones, 5, 5, 3)
+    assert np.abs(to_np(y1)[2:62, 2:62, 2:62] - 1).max() < 2e-3

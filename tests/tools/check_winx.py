@@ -14,8 +14,8 @@ from oracle import fa_oracle as fo
 from util import randn_np, rel_err, to_dev, to_np
 
 CASES = [
-    ((64,), 8, {}, 3),                                   # 1-D defaults (stride 8, pad 3): shifted boxes, 16 windows per tile
-    ((128,), 16, dict(stride=16, pad=0), 2),             # block_fa 1-D, aligned boxes (shift always 0)
+    ((256,), 32, {}, 3),                                 # 1-D defaults (stride 32, pad 15): shifted boxes, 4 windows per tile
+    ((512,), 48, dict(stride=48, pad=0), 2),             # block_fa 1-D, aligned starts, a short last group (10 windows: 8 + 2)
     ((16, 12), 7, {}, 2),                                # config-2 geometry in small: G = 2, one short group per row
     ((64, 64), 7, {}, 3),                                # config 2 (64x64, W 7, pad 3): 10 windows per row = groups of 8 + 2
     ((24, 9), 4, dict(stride=4, pad=0), 2),              # 16 slots per window, G = 8
