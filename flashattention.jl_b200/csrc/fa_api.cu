@@ -252,8 +252,22 @@ int fa_circulant_bwd(const void* q, const void* k, const void* v, const void* o,
 }
 
 // ------------------------------------------------------------------------------ windowed
+// 1-D windows LARGER than one 128-row tile (W > 128; the reference benchmarks W up to 512, logs/wind_t16.txt:7-8): a
+// window is a dense attention problem of W tokens, and with pad = 0 window w is the token range [w stride, w stride + W)
+// of the array itself.  So the dense tcgen05 kernels run on a VIEW (W, d, L) of q, k, v -- "batch element" w = window w,
+// batch stride = the window stride, read in place through the tensor map, no unfold copy -- into a (W, dv, L, B)
+// workspace (the `yw` of src/windowed.jl:8-11), and the deterministic gather-form fold finishes y = fold(yw) ./ count.
+static bool bigwin_supported(const Geo& g, int dtype, int flags) {
+  if (flags & (FA_FLAG_FORCE_SIMT | FA_FLAG_OUT_F32)) return false;
+  if (dtype != FA_BF16 && dtype != FA_F16) return false;
+  if (g.mode != MODE_WINDOWED || g.nd != 1 || g.WD <= 128 || g.padv[0] != 0) return false;
+  if (g.d != g.dv || (g.d != 32 && g.d != 64 && g.d != 128)) return false;
+  if (g.stride % 8 != 0 || g.N % 8 != 0 || g.W % 8 != 0 || g.L > 65535) return false;     // 16-byte TMA strides; gridDim.y
+  return true;
+}
 // f32out (FA_FLAG_OUT_F32): the fold accumulators are used even without overlap and finalised into float32 outputs
-static size_t windowed_fwd_ws(const Geo& g, bool f32out = false) {
+static size_t windowed_fwd_ws(const Geo& g, bool f32out = false, int dtype = FA_F32, int flags = FA_FLAG_FORCE_SIMT) {
+  if (bigwin_supported(g, dtype, flags)) return align256((size_t)g.WD * g.dv * g.L * g.B * dtype_size(dtype));
   return (g.overlap || f32out) ? align256((size_t)g.N * g.dv * g.B * sizeof(float)) : 256;
 }
 static size_t windowed_bwd_ws(const Geo& g, bool f32out = false) {
@@ -266,7 +280,7 @@ size_t fa_workspace_bytes_windowed_fwd(int ndim, const int64_t* dims, int64_t d,
                                        int64_t W, int64_t stride, int64_t pad, int dtype, int flags) {
   Geo g;
   if (windowed_geo(g, ndim, dims, d, dv, B, W, stride, pad)) return 0;
-  return windowed_fwd_ws(g, want_f32_out(dtype, flags));
+  return windowed_fwd_ws(g, want_f32_out(dtype, flags), dtype, flags);
 }
 
 static int windowed_fwd_impl(const Geo& g, const void* q, const void* k, const void* v, void* y, float* l, float* m,
@@ -276,11 +290,28 @@ static int windowed_fwd_impl(const Geo& g, const void* q, const void* k, const v
   if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
   if (!q || !k || !v || !y || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
   const bool f32out = want_f32_out(dtype, flags);
-  if ((g.overlap || f32out) && (!workspace || workspace_bytes < windowed_fwd_ws(g, f32out))) {
+  const bool bigwin = bigwin_supported(g, dtype, flags) && !(workspace == nullptr && workspace_bytes == 0);   // slab calls carry no workspace
+  if ((g.overlap || f32out || bigwin) && (!workspace || workspace_bytes < windowed_fwd_ws(g, f32out, dtype, bigwin ? flags : FA_FLAG_FORCE_SIMT))) {
     set_error("workspace too small"); return FA_ERR_WORKSPACE;
   }
   if ((rc = need_device())) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bigwin) {
+    set_path("tc");
+    Geo gd = dense_geo(g.WD, d, dv, g.L);                     // one window = one dense problem; tau = 1/sqrt(d) as src/windowed.jl:8-11
+    const size_t esz = dtype_size(dtype);
+    for (int64_t b = 0; b < B; ++b) {
+      const char* qb = static_cast<const char*>(q) + (size_t)b * g.N * d * esz;
+      const char* kb = static_cast<const char*>(k) + (size_t)b * g.N * d * esz;
+      const char* vb = static_cast<const char*>(v) + (size_t)b * g.N * dv * esz;
+      char* ow = static_cast<char*>(workspace) + (size_t)b * g.WD * dv * g.L * esz;
+      FwdArgs aw{qb, kb, vb, ow, nullptr, l + (size_t)b * g.WD * g.L, m + (size_t)b * g.WD * g.L, 0,
+                 (long long)g.N * (long long)esz, (long long)g.stride * (long long)esz};
+      if ((rc = tc_fwd(gd, aw, dtype, st))) return rc;
+    }
+    Geo gf = g; gf.d = (int)dv;                               // fold over dv channels
+    return window_scatter(gf, workspace, y, dtype, st, /*divide=*/1);      // y = fold(yw) ./ count; uncovered -> 0/0 = NaN
+  }
   FwdArgs a{q, k, v, y, nullptr, l, m};
   const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_win_supported(g, dtype);
   if (f32out && !tc) return no_f32_out();
@@ -453,6 +484,14 @@ int fa_unwindow(const void* xw, void* x, int ndim, const int64_t* dims, int64_t 
   if (!x || !xw) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
   if ((rc = need_device())) return rc;
   return window_scatter(g, xw, x, dtype, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ dtype conversion
+int fa_cast(const void* in, void* out, int64_t n, int from_dtype, int to_dtype, void* stream) {
+  if (!in || !out || n <= 0 || !valid_dtype(from_dtype) || !valid_dtype(to_dtype)) { set_error("bad fa_cast arguments"); return FA_ERR_INVALID; }
+  int rc = need_device();
+  if (rc) return rc;
+  return cast_launch(in, out, n, from_dtype, to_dtype, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------ softmax

@@ -119,6 +119,10 @@ struct FwdArgs {
   float *l, *m;
   int o_f32;        // tcgen05 dense/circulant forward only: `o` is float32 whatever the input dtype
                     // (block partials of the ring pass must not be rounded to 16 bits before merging)
+  // tcgen05 dense forward only: q, k, v are VIEWS with these byte strides between channels / batch elements instead of
+  // the dense N * 2 and N * d * 2 (0 = dense).  Used for 1-D windows larger than a tile: "batch element" w = window w,
+  // stride_b = window stride, so that overlapping windows are read in place (no unfold copy).  Multiples of 16.
+  long long in_stride_c, in_stride_b;
 };
 struct BwdArgs {
   const void *q, *k, *v, *o, *d_o;
@@ -134,7 +138,9 @@ int fold_finalize(const Geo& g, const float* acc, void* y, int channels, int dty
                   cudaStream_t st);
 int fill_uncovered_nan(const Geo& g, void* y, int channels, int dtype, cudaStream_t st);
 int window_gather(const Geo& g, const void* x, void* xw, int dtype, cudaStream_t st);
-int window_scatter(const Geo& g, const void* xw, void* x, int dtype, cudaStream_t st);
+// divide != 0: y = fold(xw) ./ count (windowed_fa, src/windowed.jl:16-19); channels = g.d
+int window_scatter(const Geo& g, const void* xw, void* x, int dtype, cudaStream_t st, int divide = 0);
+int cast_launch(const void* in, void* out, long long n, int from, int to, cudaStream_t st);
 int softmax_launch(void* out, const void* in, long long M, long long N, long long B, int dim,
                    int dtype, cudaStream_t st);
 

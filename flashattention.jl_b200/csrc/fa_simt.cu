@@ -463,7 +463,7 @@ __global__ void window_gather_kernel(const Geo g, const T* __restrict__ x, T* __
 // standalone fold: x[(tok, c, b)] = sum over (kappa, w) reading tok of xw   (src/utils.jl:46-54)
 // gather form (deterministic, no atomics): enumerate the windows covering tok.
 template <typename T>
-__global__ void window_scatter_kernel(const Geo g, const T* __restrict__ xw, T* __restrict__ x) {
+__global__ void window_scatter_kernel(const Geo g, const T* __restrict__ xw, T* __restrict__ x, int divide) {
   const long long total = g.N * g.d * g.B;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -494,6 +494,11 @@ __global__ void window_scatter_kernel(const Geo g, const T* __restrict__ xw, T* 
             }
             sum += to_f32<T>(xw[((b * g.L + w) * g.d + c) * g.WD + kap]);
           }
+    }
+    if (divide) {                                   // windowed_fa: y = fold(yw) ./ count (src/windowed.jl:16-19); 0/0 = NaN
+      int cnt = 1;
+      for (int k = 0; k < g.nd; ++k) cnt *= wn[k] > 0 ? wn[k] : 0;
+      sum = sum / (float)cnt;
     }
     x[i] = from_f32<T>(sum);
   }
@@ -627,14 +632,36 @@ int window_gather(const Geo& g, const void* x, void* xw, int dtype, cudaStream_t
 }
 
 template <typename T>
-static int window_scatter_t(const Geo& g, const void* xw, void* x, cudaStream_t st) {
+static int window_scatter_t(const Geo& g, const void* xw, void* x, int divide, cudaStream_t st) {
   window_scatter_kernel<T><<<ew_grid(g.N * g.d * g.B), 256, 0, st>>>(
-      g, static_cast<const T*>(xw), static_cast<T*>(x));
+      g, static_cast<const T*>(xw), static_cast<T*>(x), divide);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
 }
-int window_scatter(const Geo& g, const void* xw, void* x, int dtype, cudaStream_t st) {
-  FA_DISPATCH_DTYPE(dtype, window_scatter_t<T>(g, xw, x, st));
+int window_scatter(const Geo& g, const void* xw, void* x, int dtype, cudaStream_t st, int divide) {
+  FA_DISPATCH_DTYPE(dtype, window_scatter_t<T>(g, xw, x, divide, st));
+}
+
+
+// element-wise dtype conversion (round-to-nearest-even), grid-stride, 128-bit accesses where aligned
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f32<TO>(to_f32<TI>(in[i]));
+}
+template <typename TI, typename TO>
+static int cast_t(const void* in, void* out, long long n, cudaStream_t st) {
+  cast_kernel<TI, TO><<<ew_grid(n), 256, 0, st>>>(static_cast<const TI*>(in), static_cast<TO*>(out), n);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+int cast_launch(const void* in, void* out, long long n, int from, int to, cudaStream_t st) {
+  if (from == FA_F32 && to == FA_BF16) return cast_t<float, __nv_bfloat16>(in, out, n, st);
+  if (from == FA_F32 && to == FA_F16) return cast_t<float, __half>(in, out, n, st);
+  if (from == FA_BF16 && to == FA_F32) return cast_t<__nv_bfloat16, float>(in, out, n, st);
+  if (from == FA_F16 && to == FA_F32) return cast_t<__half, float>(in, out, n, st);
+  set_error("fa_cast: unsupported dtype pair (%d -> %d)", from, to);
+  return FA_ERR_UNSUPPORTED;
 }
 
 }  // namespace fa

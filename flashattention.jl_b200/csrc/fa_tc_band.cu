@@ -39,7 +39,7 @@
 
 namespace fa {
 
-int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B);
+int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B, long long stride_c = 0, long long stride_b = 0);
 
 namespace {
 
@@ -62,7 +62,7 @@ template <int CTAS, int D> struct BandCfg {
                        BAR_OFINAL = BAR_PFULL + 1, NUM_BARS = BAR_OFINAL + 1;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_SLOT + 16 + 1024;
-  static constexpr int TMEM_COLS = D == 64 ? 128 : 256, COL_S = 0, COL_O = 64;
+  static constexpr int TMEM_COLS = D <= 64 ? 128 : 256, COL_S = 0, COL_O = 64;
   static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory for CTAS CTAs per SM");
   static_assert(CTAS_PER_SM * TMEM_COLS <= 512, "TMEM");
 };
@@ -523,9 +523,9 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
   using C = BandCfg<CTAS, D>;
   CUtensorMap tmq, tmk, tmv;
   int rc;
-  if ((rc = make_tmap_public(&tmq, a.q, dtype, g.N, D, g.B))) return rc;
-  if ((rc = make_tmap_public(&tmk, a.k, dtype, g.N, D, g.B))) return rc;
-  if ((rc = make_tmap_public(&tmv, a.v, dtype, g.N, D, g.B))) return rc;
+  if ((rc = make_tmap_public(&tmq, a.q, dtype, g.N, D, g.B, a.in_stride_c, a.in_stride_b))) return rc;
+  if ((rc = make_tmap_public(&tmk, a.k, dtype, g.N, D, g.B, a.in_stride_c, a.in_stride_b))) return rc;
+  if ((rc = make_tmap_public(&tmv, a.v, dtype, g.N, D, g.B, a.in_stride_c, a.in_stride_b))) return rc;
   BandParams prm;
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.W = g.W; prm.p = g.p;
@@ -548,6 +548,10 @@ int launch_band(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st, int 
 // circulant, d = dv in {64, 128}, 16-bit output, tile-aligned wrap-around (N % 64 == 0) -- checked by the caller (tc_fwd)
 int tc_band_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   static const int ctas = [] { const char* e = getenv("FA_BAND_CTAS"); return e ? atoi(e) : 4; }();
+  if (g.d == 32) {      // the reference's benchmark head dim (logs/circ_t*.txt, logs/wind_t*.txt): same kernel, two K steps per QK
+    if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 4, 2, 32, 1>(g, a, dtype, st) : launch_band<0, 4, 2, 32, 1>(g, a, dtype, st);
+    return dtype == FA_BF16 ? launch_band<1, 4, 0, 32>(g, a, dtype, st) : launch_band<0, 4, 0, 32>(g, a, dtype, st);
+  }
   if (g.d == 128) {
     if (g.mode == MODE_DENSE) return dtype == FA_BF16 ? launch_band<1, 2, 2, 128>(g, a, dtype, st) : launch_band<0, 2, 2, 128>(g, a, dtype, st);
     return dtype == FA_BF16 ? launch_band<1, 2, 0, 128>(g, a, dtype, st) : launch_band<0, 2, 0, 128>(g, a, dtype, st);

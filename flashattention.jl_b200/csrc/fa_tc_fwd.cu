@@ -839,11 +839,11 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // tensor map over one [B][D][N] tensor: box = 64 tokens x D channels x 1 batch, SWIZZLE_128B
-int make_tmap(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B) {
+int make_tmap(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B, long long stride_c = 0, long long stride_b = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return FA_ERR_CUDA; }
   const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)D, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {(cuuint64_t)N * 2, (cuuint64_t)N * D * 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)(stride_c ? stride_c : N * 2), (cuuint64_t)(stride_b ? stride_b : N * D * 2)};
   const cuuint32_t box[3] = {64, (cuuint32_t)D, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapDataType dt = dtype == FA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -857,9 +857,9 @@ template <int D, int FMT, int NQT, int SPLIT = 1>
 int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   CUtensorMap tmq, tmk, tmv;
   int rc;
-  if ((rc = make_tmap(&tmq, a.q, dtype, g.N, D, g.B))) return rc;
-  if ((rc = make_tmap(&tmk, a.k, dtype, g.N, D, g.B))) return rc;
-  if ((rc = make_tmap(&tmv, a.v, dtype, g.N, D, g.B))) return rc;
+  if ((rc = make_tmap(&tmq, a.q, dtype, g.N, D, g.B, a.in_stride_c, a.in_stride_b))) return rc;
+  if ((rc = make_tmap(&tmk, a.k, dtype, g.N, D, g.B, a.in_stride_c, a.in_stride_b))) return rc;
+  if ((rc = make_tmap(&tmv, a.v, dtype, g.N, D, g.B, a.in_stride_c, a.in_stride_b))) return rc;
   TcParams prm;
   prm.o = a.o; prm.l = a.l; prm.m = a.m;
   prm.N = (int)g.N; prm.B = (int)g.B; prm.W = g.W; prm.p = g.p; prm.mode = g.mode;
@@ -885,14 +885,14 @@ int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
 
 }  // namespace
 
-int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B) {
-  return make_tmap(tm, base, dtype, N, D, B);
+int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B, long long stride_c, long long stride_b) {
+  return make_tmap(tm, base, dtype, N, D, B, stride_c, stride_b);
 }
 
 bool tc_fwd_supported(const Geo& g, int dtype) {
   if (dtype != FA_BF16 && dtype != FA_F16) return false;
   if (g.mode != MODE_DENSE && g.mode != MODE_CIRCULANT) return false;
-  if (g.d != g.dv || (g.d != 64 && g.d != 128)) return false;
+  if (g.d != g.dv || (g.d != 32 && g.d != 64 && g.d != 128)) return false;
   if (g.N % 8 != 0 || g.N < 8 || g.N > 0x3fffffff) return false;    // TMA: 16-byte global strides
   if (g.B > 65535) return false;                                     // gridDim.y
   if (g.mode == MODE_CIRCULANT && (g.N % 64 != 0)) return false;     // tile-aligned wrap-around
@@ -905,6 +905,10 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
     set_error("tc_fwd: q/k/v must be 16-byte aligned"); return FA_ERR_INVALID;
   }
   const int fmt = dtype == FA_BF16 ? 1 : 0;
+  if (g.d == 32) {      // d = 32 (the reference's logged benchmark head dim) exists on the band kernel only
+    if (a.o_f32) { set_error("FA_FLAG_OUT_F32 needs a shape the tcgen05 kernels cover with float32 output (d in {64,128})"); return FA_ERR_UNSUPPORTED; }
+    return tc_band_fwd(g, a, dtype, st);
+  }
   // short key loops (circulant with a band of a few tiles): one Q tile per CTA, two CTAs per SM
   const bool short_loop = g.mode == MODE_CIRCULANT && (256 + g.W) / 64 <= 24;
   if (short_loop) {

@@ -34,7 +34,7 @@ using namespace ptx;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int MAXE = 640;      // table entries per CTA iteration (20 warp-items); sized so that 2 CTAs fit one SM
-constexpr int CB = 64;         // channels per gather / scatter unit (64 loads in flight per lane)
+constexpr int CBMAX = 64;      // channels per gather / scatter unit (64 loads in flight per lane); d = 32: one unit of 32
 
 template <int FMT> struct El { using type = __half; };
 template <> struct El<1> { using type = __nv_bfloat16; };
@@ -131,13 +131,14 @@ template <int D, int NT, int TMAG = 0> struct WCfg {
   static constexpr int OFF_WIN = OFF_ROW + MAXE * 4;         // int4[256] window origins
   static constexpr int OFF_BAR = OFF_WIN + 256 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
-  static constexpr int COLS_PER_TILE = (D == 64) ? 128 : 256;
+  static constexpr int COLS_PER_TILE = (D <= 64) ? 128 : 256;
   static constexpr int TMEM_COLS = COLS_PER_TILE * NT;
-  static constexpr int COL_O = (D == 64) ? 64 : 128;         // P (64 cols) aliases S; O beside / after it
+  static constexpr int COL_O = (D <= 64) ? 64 : 128;         // P (64 cols) aliases S; O beside / after it
   // 228 KB of shared memory per SM, 1 KB of it reserved per resident CTA
   static constexpr int BY_SMEM = 228 * 1024 / (SMEM_BYTES + 1024);
   static constexpr int CTAS_PER_SM = 512 / TMEM_COLS < BY_SMEM ? 512 / TMEM_COLS : BY_SMEM;
   static_assert(TMAG || NT != 2 || D != 64 || CTAS_PER_SM == 2, "d = 64 pair kernel must fit twice per SM");
+  static_assert(D == 32 || D == 64 || D == 128, "head dims of the tcgen05 windowed kernels");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -220,6 +221,7 @@ tc_win_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant
                   const __grid_constant__ CUtensorMap tmv, const WinParams prm, const TmaGeo tg) {
   using C = WCfg<D, NT, TMAG>;
   using T = typename El<FMT>::type;
+  constexpr int CB = D < CBMAX ? D : CBMAX;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sptr);
@@ -574,10 +576,10 @@ template <int D> struct WBCfg {
   static constexpr int OFF_WIN = OFF_AMAX + 16;              // int4[128] window origins
   static constexpr int OFF_BAR = OFF_WIN + 128 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;
-  static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;
+  static constexpr int TMEM_COLS = (D <= 64) ? 256 : 512;
   static constexpr int COL_T1 = 0, COL_T2 = 128, COL_DQ = 0;
-  static constexpr int COL_DV = (D == 64) ? 64 : 256, COL_DK = (D == 64) ? 192 : 384;
-  static constexpr int CTAS_PER_SM = (D == 64) ? 2 : 1;
+  static constexpr int COL_DV = (D <= 64) ? 64 : 256, COL_DK = (D <= 64) ? 192 : 384;
+  static constexpr int CTAS_PER_SM = (D <= 64) ? 2 : 1;
 };
 
 struct WinBwdParams {
@@ -611,6 +613,7 @@ __global__ void __launch_bounds__(128, WBCfg<D>::CTAS_PER_SM)
 tc_win_bwd_kernel(const WinBwdParams prm) {
   using C = WBCfg<D>;
   using T = typename El<INBF>::type;
+  constexpr int CB = D < CBMAX ? D : CBMAX;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sptr);
@@ -1062,13 +1065,14 @@ int tc_win_bwd(const Geo& g, const BwdArgs& a, int dtype, cudaStream_t st) {
   if (!tc_win_bwd_supported(g, dtype)) { set_error("tc_win_bwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
   const int bf = dtype == FA_BF16 ? 1 : 0;
   if (g.d == 128) return bf ? launch_win_bwd<128, 1>(g, a, st) : launch_win_bwd<128, 0>(g, a, st);
+  if (g.d == 32) return bf ? launch_win_bwd<32, 1>(g, a, st) : launch_win_bwd<32, 0>(g, a, st);
   return bf ? launch_win_bwd<64, 1>(g, a, st) : launch_win_bwd<64, 0>(g, a, st);
 }
 
 bool tc_win_supported(const Geo& g, int dtype) {
   if (dtype != FA_BF16 && dtype != FA_F16) return false;
   if (g.mode != MODE_WINDOWED) return false;
-  if (g.d != g.dv || (g.d != 64 && g.d != 128)) return false;
+  if (g.d != g.dv || (g.d != 32 && g.d != 64 && g.d != 128)) return false;
   if (g.WD > 128 || g.WD < 1) return false;
   WinMap mp;
   return make_map(g, 2, mp);
@@ -1096,6 +1100,7 @@ int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
     }
   }
   if (g.d == 128) return fmt ? launch_win_fwd<128, 1, 1>(g, a, st) : launch_win_fwd<128, 1, 0>(g, a, st);
+  if (g.d == 32) return fmt ? launch_win_fwd<32, 2, 1>(g, a, st) : launch_win_fwd<32, 2, 0>(g, a, st);     // the reference's benchmark head dim (logs/wind_t*.txt)
   // d = 64: two 128-row tiles per CTA (2 CTAs / SM; longer x-runs per gather) or one tile per CTA (3 CTAs / SM).
   // Small problems -- fewer than two pair-groups per resident CTA -- are latency bound and take the finer split
   // (config 2: 19.0 -> 15.0 us); large ones keep the pair kernel (config 5: 0.93 vs 0.99 ms).  FA_WIN_NT overrides.

@@ -89,6 +89,7 @@ def _load():
         "fa_window": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_unwindow": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_softmax": (ci, [vp, vp, i64, i64, i64, ci, ci, vp]),
+        "fa_cast": (ci, [vp, vp, i64, ci, ci, vp]),
         "fa_dense_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, ci, ci, ci]),
         "fa_circulant_fwd_host": (ci, [vp] * 6 + [i64, i64, i64, i64, i64, ci, ci, ci]),
         "fa_windowed_fwd_host": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, ci, ci, ci]),
@@ -121,7 +122,7 @@ EXPORTED_SYMBOLS = (
     "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd "
     "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd "
     "fa_workspace_bytes_circulant2d_bwd_ex fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd "
-    "fa_dense_bwd_host fa_circulant_bwd_host fa_windowed_bwd_host fa_host_alloc fa_host_free").split()
+    "fa_dense_bwd_host fa_circulant_bwd_host fa_windowed_bwd_host fa_host_alloc fa_host_free fa_cast").split()
 
 
 def _check(rc: int, what: str):
@@ -263,6 +264,28 @@ def _check_out(name: str, t: torch.Tensor, shape, dtype, like: torch.Tensor):
         raise FaError(f"{name} must be dense column-major (see jl_empty)")
 
 
+def cast(x: torch.Tensor, dtype) -> torch.Tensor:
+    """``T.(x)`` on the device through ``fa_cast`` (round to nearest even), same Julia shape and layout."""
+    x = jl_array(x)
+    if x.dtype == dtype:
+        return x
+    out = jl_empty(x.shape, dtype, x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.fa_cast(_ptr(x), _ptr(out), x.numel(), _dt(x), _DTYPES[dtype], _stream(x)), "fa_cast")
+    return out
+
+
+def _via(via, flags, *ts):
+    """Float32 arrays on the tensor cores (opt-in, ``via=torch.bfloat16`` / ``torch.float16``): inputs are cast on the
+    device, the tcgen05 kernels run in that type with float32 outputs (FA_FLAG_OUT_F32), i.e. results of the 16-bit
+    compute class (2e-3) in Float32 arrays -- what a caller of bench/compare.jl:8-10 holding Float32 arrays can ask for."""
+    if via is None or ts[0].dtype != torch.float32:
+        return flags, ts
+    if via not in (torch.bfloat16, torch.float16):
+        raise FaError("via must be torch.bfloat16 or torch.float16")
+    return flags | FA_FLAG_OUT_F32, tuple(cast(t, via) for t in ts)
+
+
 def _cur_dev() -> int:
     # host entry points: the library itself reports FA_ERR_CUDA when there is no device
     return torch.cuda.current_device() if torch.cuda.is_available() else 0
@@ -292,10 +315,12 @@ def dense_fa_(O, l, m, Q, K, V, flags: int = 0):
     return O, l, m
 
 
-def dense_fa(q, k, v, flags: int = 0):
+def dense_fa(q, k, v, flags: int = 0, via=None):
     """``dense_fa(q, k, v) -> (y, l, m)`` (src/dense.jl:1-19): flattens the spatial dims,
-    allocates, calls :func:`dense_fa_`, reshapes back.  ``l, m :: (N, 1, B)`` in float32."""
+    allocates, calls :func:`dense_fa_`, reshapes back.  ``l, m :: (N, 1, B)`` in float32.
+    ``via=torch.bfloat16``: Float32 CUDA arrays on the tensor cores (see :func:`_via`)."""
     _same(q, k, v)
+    flags, (q, k, v) = _via(via, flags, q, k, v)
     q, k, v = (jl_array(t) for t in (q, k, v))
     N, d, B = _flatten3(q)
     dv = int(v.shape[-2])
@@ -441,11 +466,12 @@ def window_counts(spatial, W, stride=None, pad=None):
     return tuple(int(x) for x in nw)
 
 
-def windowed_fa(q, k, v, windowsize: int, stride: Optional[int] = None, pad: Optional[int] = None, flags: int = 0):
+def windowed_fa(q, k, v, windowsize: int, stride: Optional[int] = None, pad: Optional[int] = None, flags: int = 0, via=None):
     """``windowed_fa(q, k, v, W; stride=W, pad=(W-1)/2) -> (y, l, m)`` (src/windowed.jl:3-23):
     window-partition attention with zero padding and fold-averaging, the unfold/fold of
     src/utils.jl:36-54 fused into the kernel.  ``l, m :: (W^D, 1, L, B)`` float32."""
     _same(q, k, v)
+    flags, (q, k, v) = _via(via, flags, q, k, v)
     q, k, v = (jl_array(t) for t in (q, k, v))
     W = int(windowsize)
     stride, pad = _win_kws(W, stride, pad)
@@ -665,9 +691,10 @@ def circulant_fa_(O, l, m, Q, K, V, W: int, flags: int = 0):
     return O, l, m
 
 
-def circulant_fa(Q, K, V, W: int, flags: int = 0):
+def circulant_fa(Q, K, V, W: int, flags: int = 0, via=None):
     """``circulant_fa(Q, K, V, W)``: allocating wrapper.  The reference's drops ``W``
     (src/circulant.jl:6, SURVEY B-1); this one passes it."""
+    flags, (Q, K, V) = _via(via, flags, Q, K, V)
     if Q.ndim == 4:
         X, Y, d, B = (int(s) for s in Q.shape)
         O = jl_empty((X, Y, int(V.shape[2]), B), Q.dtype, Q.device)

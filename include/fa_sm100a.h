@@ -172,6 +172,12 @@ int fa_window(const void* x, void* xw, int ndim, const int64_t* dims, int64_t d,
 int fa_unwindow(const void* xw, void* x, int ndim, const int64_t* dims, int64_t d, int64_t B,
                 int64_t W, int64_t stride, int64_t pad, int dtype, void* stream);
 
+/* ---- element-wise dtype conversion (round to nearest even): F32 <-> F16 / BF16.  The host layer uses it for the opt-in
+ *      "Float32 arrays on the tensor cores" mode (Julia: dense_fa(q, k, v; via = BFloat16); Python: via=torch.bfloat16):
+ *      cast q, k, v, run the tcgen05 kernels with FA_FLAG_OUT_F32, i.e. bf16/fp16 compute class (2e-3) for callers
+ *      that hold Float32 arrays as bench/compare.jl:8-10 does. */
+int fa_cast(const void* in, void* out, int64_t n, int from_dtype, int to_dtype, void* stream);
+
 /* ---- softmax: replaces fused_softmax! (src/fused_softmax.jl:11-39); in :: (M,N,B) column-major,
  *      dim = 1 (columns) or 2 (rows); any other dim -> FA_ERR_INVALID (assertion at :12) */
 int fa_softmax(void* out, const void* in, int64_t M, int64_t N, int64_t B, int dim, int dtype,

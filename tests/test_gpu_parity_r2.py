@@ -283,3 +283,79 @@ def test_windowed_streamed_kernel_default_dispatch_config5_batch():
     ones = fa.jl_empty((64, 64, 64, 64, B), BF16).fill_(1)
     y1, _, _ = fa.windowed_fa(Q, K, ones, 5, 5, 3)
     assert np.abs(to_np(y1)[2:62, 2:62, 2:62] - 1).max() < 2e-3
+
+
+# ------------------------------------------------------------------------------- d = 32: the reference's logged benchmark head dim
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("N,B", [(256, 2), (1024, 1), (200, 1), (4096, 1)])
+def test_dense_fwd_tc_d32(N, B, dtype):
+    q, k, v = (randn_np((N, 32, B), s, dtype) for s in range(3))
+    y, l, m = fa.dense_fa(*(to_dev(t, dtype) for t in (q, k, v)))
+    assert fa.last_path() == "tc"
+    y0, l0, m0 = fo.dense_fa(*f64(q, k, v))
+    assert rel_err(to_np(y), y0, dtype) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+    assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
+
+
+@pytest.mark.parametrize("W", [16, 32, 64, 128, 256, 512, 1024])
+def test_circulant_fwd_tc_d32_logged_shapes(W):
+    """logs/circ_t16.txt:3-9 (runcirculant, bench/compare.jl:119-129): N = 4096, d = 32, bs = 1, W = 16 .. 1024 (even
+    windows: one extra key on the right) -- on the tcgen05 band kernel."""
+    q, k, v = (randn_np((4096, 32, 1), s, BF16) for s in range(3))
+    O, l, m = fa.circulant_fa(*(to_dev(t, BF16) for t in (q, k, v)), W)
+    assert fa.last_path() == "tc"
+    O0, l0, m0 = fo.circulant_fa(*f64(q, k, v), W)
+    assert rel_err(to_np(O), O0, BF16) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+
+
+@pytest.mark.parametrize("W", [16, 32, 64, 128, 256, 512])
+def test_windowed_fwd_tc_d32_logged_shapes(W):
+    """logs/wind_t16.txt:3-8 (runwindow, bench/compare.jl:106-117): N = 4096, d = 32, bs = 1, stride 8, pad 0,
+    W = 16 .. 512 (overlapping windows: fold-sum / count) -- on the tensor-core path, forward; backward for W <= 128."""
+    q, k, v, g = (randn_np((4096, 32, 1), s, BF16) for s in range(4))
+    Q, K, V, G = (to_dev(t, BF16) for t in (q, k, v, g))
+    y, l, m = fa.windowed_fa(Q, K, V, W, stride=8, pad=0)
+    assert fa.last_path() == "tc"
+    y0, l0, m0 = fo.windowed_fa(*f64(q, k, v), W, stride=8, pad=0)
+    assert tuple(l.shape) == l0.shape
+    assert rel_err(to_np(y), y0, BF16) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+    if W <= 128:
+        got = fa.windowed_fa_backward(Q, K, V, G, l, m, W, stride=8, pad=0)
+        assert fa.last_path() == "tc"
+        want = fo.windowed_backward(*f64(q, k, v, g), W, stride=8, pad=0)
+        for a, b_ in zip(got, want):
+            assert rel_err(to_np(a), b_, BF16) < 2e-3
+
+
+@pytest.mark.parametrize("W,kws", [(64, dict(stride=64, pad=0)), (64, dict(stride=16, pad=0))])
+def test_compare1_shapes_d64(W, kws):
+    """logs/compare1.txt (runcompare, bench/compare.jl:86-104, d = 64, windowsize = 64): block_fa and windowed_fa
+    (stride 16) at N = 1024 on the tcgen05 path."""
+    q, k, v = (randn_np((1024, 64, 1), s, BF16) for s in range(3))
+    y, l, m = fa.windowed_fa(*(to_dev(t, BF16) for t in (q, k, v)), W, **kws)
+    assert fa.last_path() == "tc"
+    y0, l0, m0 = fo.windowed_fa(*f64(q, k, v), W, **kws)
+    assert rel_err(to_np(y), y0, BF16) < 2e-3 and rel_err(to_np(l), l0) < 2e-3
+
+
+# ------------------------------------------------------------------------------- Float32 arrays on the tensor cores (opt-in)
+@pytest.mark.parametrize("via", [BF16, F16])
+def test_float32_arrays_via_16bit_tensor_cores(via):
+    """`via=`: Float32 CUDA arrays are cast on the device (fa_cast) and run on the tcgen05 kernels with float32 outputs;
+    results are those of the 16-bit compute class: 2e-3 against the oracle on the ROUNDED inputs (what the kernel sees),
+    and a looser, stated bound against the oracle on the original Float32 inputs (input rounding included)."""
+    q, k, v = (randn_np((1024, 64, 2), s, F32) for s in range(3))
+    Q, K, V = (to_dev(t, F32) for t in (q, k, v))
+    y, l, m = fa.dense_fa(Q, K, V, via=via)
+    assert fa.last_path() == "tc" and y.dtype == F32
+    rq, rk, rv = (torch.from_numpy(np.ascontiguousarray(t)).to(via).double().numpy() for t in (q, k, v))
+    y0, l0, m0 = fo.dense_fa(*(np.asfortranarray(t) for t in (rq, rk, rv)))
+    assert rel_err(to_np(y), y0) < RAW_FWD_TOL[via] and rel_err(to_np(l), l0) < 2e-3
+    y1, _, _ = fo.dense_fa(*f64(q, k, v))
+    assert rel_err(to_np(y), y1) < (2e-2 if via == BF16 else 4e-3)
+    yw, lw, mw = fa.windowed_fa(*(to_dev(randn_np((20, 12, 64, 2), s, F32), F32) for s in range(3)), 7, via=via)
+    assert fa.last_path() == "tc" and yw.dtype == F32
+    O, _, _ = fa.circulant_fa(Q, K, V, 65, via=via)
+    assert fa.last_path() == "tc" and O.dtype == F32
+    O0, _, _ = fo.circulant_fa(*(np.asfortranarray(t) for t in (rq, rk, rv)), 65)
+    assert rel_err(to_np(O), O0) < RAW_FWD_TOL[via]
