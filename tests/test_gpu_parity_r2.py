@@ -269,7 +269,8 @@ def test_windowed_streamed_kernel_default_dispatch_config5_batch():
     yy = to_np(y)
     rng = np.random.default_rng(3)
     for _ in range(24):
-        wx, wy, wz, b = (int(rng.integers(0, 14)) for _ in range(3)) + (int(rng.integers(0, B)),)
+        wx, wy, wz = (int(rng.integers(0, 14)) for _ in range(3))
+        b = int(rng.integers(0, B))
         lo = [5 * w - 3 for w in (wx, wy, wz)]
         sl = tuple(slice(max(0, a), min(64, a + 5)) for a in lo)
         qs, ks, vs = (np.asfortranarray(t[sl + (slice(None), slice(b, b + 1))].astype(np.float64)) for t in (q, k, v))

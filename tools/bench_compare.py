@@ -2,7 +2,8 @@
 path, printed beside the reference's logged CPU numbers (logs/compare1.txt:3-9, logs/wind_t16.txt:3-8,
 logs/circ_t16.txt:3-9; Float64, seconds per call, CPU model unrecorded).  GPU: bf16 on the tcgen05 kernels (and the
 exact Float32 kernels with --f32), CUDA-event time per call over `reps` calls after a warm-up that also checks fa against
-the naive dpa form (bench/compare.jl:19-20,45-47,72-74).  One JSON line per row.
+the naive dpa form (bench/compare.jl:19-20,45-47,72-74); `graph_s` = the same call replayed 20x from one CUDA graph (GPU
+time without the host wrapper: the bs = 1 problems of the reference's tables are launch-latency bound).  One JSON line per row.
   python tools/bench_compare.py [--reps 50] [--f32]"""
 import argparse, json, os, sys
 import torch
@@ -37,6 +38,23 @@ def timeit(fn):
     return e0.elapsed_time(e1) / a.reps * 1e-3
 
 
+def graph_time(fn, reps=20):
+    """GPU time per call without the Python wrapper / launch latency: `reps` calls captured in one CUDA graph."""
+    fn(); torch.cuda.synchronize()
+    st_ = torch.cuda.Stream()
+    with torch.cuda.stream(st_):
+        fn()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_, stream=st_):
+            for _ in range(reps):
+                fn()
+    torch.cuda.synchronize()
+    g_.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g_.replay(); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
 def close(x, y, tol=2e-2):
     x, y = x.float(), y.float()
     return float((x - y).abs().max() / y.abs().max()) < tol
@@ -58,16 +76,20 @@ for N, ref in COMPARE1.items():                      # runcompare(N_range = 2 .^
     tc = timeit(lambda: fa.circulant_fa(q, k, v, 65)); pc = fa.last_path()
     print(json.dumps({"table": "compare1", "N": N, "d": 64, "bs": 1, "dtype": str(dt)[6:],
                       "dense_fa_s": td, "block_fa_s": tb, "wind_fa_s": tw, "circ_fa_s": tc, "paths": [pd, pb, pw, pc],
+                      "graph_s": [graph_time(lambda: fa.dense_fa(q, k, v)), graph_time(lambda: fa.block_fa(q, k, v, 64)),
+                                  graph_time(lambda: fa.windowed_fa(q, k, v, 64, stride=16, pad=0)), graph_time(lambda: fa.circulant_fa(q, k, v, 65))],
                       "ref_cpu_f64_s": ref, "speedup": [r / t for r, t in zip(ref, (td, tb, tw, tc))]}), flush=True)
 for W, ref in WIND_T16.items():                      # runwindow(2 .^ (4:9)): N = 4096, d = 32, stride 8, pad 0
     q, k, v = qkv(4096, 32)
     assert close(fa.windowed_fa(q, k, v, W, stride=8, pad=0)[0], fa.windowed_dpa(q, k, v, W, stride=8, pad=0)[0])
     t = timeit(lambda: fa.windowed_fa(q, k, v, W, stride=8, pad=0))
     print(json.dumps({"table": "wind_t16", "N": 4096, "d": 32, "W": W, "stride": 8, "dtype": str(dt)[6:], "wind_fa_s": t,
+                      "graph_s": graph_time(lambda: fa.windowed_fa(q, k, v, W, stride=8, pad=0)),
                       "path": fa.last_path(), "ref_cpu_f64_16thr_s": ref, "speedup": ref / t}), flush=True)
 for W, ref in CIRC_T16.items():                      # runcirculant(2 .^ (4:10)): N = 4096, d = 32
     q, k, v = qkv(4096, 32)
     assert close(fa.circulant_fa(q, k, v, W)[0], fa.circulant_dpa(q, k, v, W)[0])
     t = timeit(lambda: fa.circulant_fa(q, k, v, W))
     print(json.dumps({"table": "circ_t16", "N": 4096, "d": 32, "W": W, "dtype": str(dt)[6:], "circ_fa_s": t,
+                      "graph_s": graph_time(lambda: fa.circulant_fa(q, k, v, W)),
                       "path": fa.last_path(), "ref_cpu_f64_16thr_s": ref, "speedup": ref / t}), flush=True)
