@@ -463,6 +463,73 @@ int fa_windowed_slab_bwd(const void* q, const void* k, const void* v, const void
   return windowed_bwd_impl(g, q, k, v, d_y, l, m, dq, dk, dv_out, dtype, flags, workspace, workspace_bytes, stream);
 }
 
+// ------------------------------------------------------------------------------ windowed, one volume, OVERLAPPING windows
+// "overlapping windows -> halo of W - stride planes of K/V in, partial-y halo reduce out".  Window planes
+// are dealt out by their START plane, so a rank's windows read its own planes plus up to W - stride planes of the NEXT
+// rank (the halo in); it then holds fold SUMS for all those planes, the halo part of which belongs to the next rank
+// (the halo reduce out); the owner divides by the window count of the whole volume.  The two exchanges are the host
+// layer's (fa_sm100a/halo.py over torch.distributed, julia/../multigpu.jl over NCCL.jl); this file supplies the plan,
+// the un-normalised slab forward and the final division.
+int fa_windowed_halo_plan(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                          int rank, int nranks, int64_t* plan) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, 1, 1, 1, W, stride, pad);
+  if (rc) return rc;
+  if (!plan || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bad rank / nranks / plan"); return FA_ERR_INVALID; }
+  if (pad >= W) { set_error("halo split needs pad < W"); return FA_ERR_UNSUPPORTED; }
+  const int ks = ndim - 1;
+  const int64_t S = dims[ks], nw = g.o[ks];
+  int64_t lo = 0, cnt = 0;
+  if ((rc = fa_shard_batch(nw, nranks, rank, &lo, &cnt))) return rc;
+  const int64_t hi = lo + cnt;
+  auto clip = [&](int64_t x) { return x < 0 ? (int64_t)0 : (x > S ? S : x); };
+  // plan = {own_lo, own_hi, ext_hi, win_lo, win_hi, pad_lo}: owned planes [own_lo, own_hi) tile the volume; the windows
+  // [win_lo, win_hi) read planes [own_lo, ext_hi) (ext_hi - own_hi halo planes of the next rank), the first of them
+  // starting pad_lo planes in front of own_lo
+  plan[3] = lo; plan[4] = hi;
+  if (cnt <= 0) { plan[0] = plan[1] = plan[2] = (lo >= nw ? S : clip(lo * stride - pad)); plan[5] = 0; return FA_OK; }
+  plan[0] = lo == 0 ? 0 : clip(lo * stride - pad);
+  plan[1] = hi == nw ? S : clip(hi * stride - pad);
+  plan[2] = clip((hi - 1) * stride - pad + W);
+  if (plan[2] < plan[1]) plan[2] = plan[1];
+  plan[5] = plan[0] - (lo * stride - pad);
+  return FA_OK;
+}
+
+int fa_windowed_slab_fwd_sums(const void* q, const void* k, const void* v, float* acc, float* l, float* m,
+                              int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                              int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
+                              int dtype, int flags, void* stream) {
+  Geo g;
+  if (pad_lo < 0) { set_error("slab: pad_lo must be >= 0"); return FA_ERR_INVALID; }
+  int rc = windowed_geo(g, ndim, slab_dims, d, dv, B, W, stride, pad, pad_lo, nwin);
+  if (rc) return rc;
+  if ((rc = check_common(g.N, d, dv, B, dtype))) return rc;
+  if (!q || !k || !v || !acc || !l || !m) { set_error("NULL tensor pointer"); return FA_ERR_INVALID; }
+  if ((rc = need_device())) return rc;
+  g.overlap = 1;                                            // always the accumulating (fold-sum) form
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FwdArgs a{q, k, v, nullptr, acc, l, m};
+  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_win_supported(g, dtype);
+  set_path(tc ? "tc" : "simt");
+  FA_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)g.N * dv * B * sizeof(float), st));
+  return tc ? tc_win_fwd(g, a, dtype, st) : simt_fwd(g, a, dtype, st);
+}
+
+int fa_window_divide(const float* acc, void* y, int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                     int64_t plane_lo, int64_t nplanes, int64_t channels, int64_t B, int dtype, void* stream) {
+  Geo g;
+  int rc = windowed_geo(g, ndim, dims, channels, channels, B, W, stride, pad);
+  if (rc) return rc;
+  if (!acc || !y || !valid_dtype(dtype) || channels <= 0 || B <= 0 || plane_lo < 0 || nplanes <= 0 || plane_lo + nplanes > dims[ndim - 1]) {
+    set_error("bad fa_window_divide arguments"); return FA_ERR_INVALID;
+  }
+  if ((rc = need_device())) return rc;
+  long long plane_tokens = 1;
+  for (int k = 0; k < ndim - 1; ++k) plane_tokens *= dims[k];
+  return slab_divide(g, acc, y, (int)channels, dtype, plane_lo, plane_tokens * nplanes, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------ unfold / fold
 int fa_window(const void* x, void* xw, int ndim, const int64_t* dims, int64_t d, int64_t B,
               int64_t W, int64_t stride, int64_t pad, int dtype, void* stream) {

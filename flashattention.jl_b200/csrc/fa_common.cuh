@@ -117,7 +117,8 @@ struct FwdArgs {
   void* o;          // dense/circulant: output; windowed non-overlap: y; windowed overlap: unused
   float* acc;       // windowed overlap: fp32 fold accumulator (N*dv*B), zero-initialised
   float *l, *m;
-  int o_f32;        // tcgen05 dense/circulant forward only: `o` is float32 whatever the input dtype
+  int o_f32;        // tcgen05 dense/circulant forward only: 1 = `o` is float32 whatever the input dtype; 2 (pair kernel) =
+                    // `o`, `l`, `m` hold a running (O, l, m) and this call's result is MERGED into them (ring pass)
                     // (block partials of the ring pass must not be rounded to 16 bits before merging)
   // tcgen05 dense forward only: q, k, v are VIEWS with these byte strides between channels / batch elements instead of
   // the dense N * 2 and N * d * 2 (0 = dense).  Used for 1-D windows larger than a tile: "batch element" w = window w,
@@ -136,6 +137,7 @@ int simt_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
 int simt_bwd(const Geo& g, const BwdArgs& a, int dtype, cudaStream_t st);
 int fold_finalize(const Geo& g, const float* acc, void* y, int channels, int dtype, int divide,
                   cudaStream_t st);
+int slab_divide(const Geo& g, const float* acc, void* y, int channels, int dtype, long long plane_lo, long long slab_tokens, cudaStream_t st);
 int fill_uncovered_nan(const Geo& g, void* y, int channels, int dtype, cudaStream_t st);
 int window_gather(const Geo& g, const void* x, void* xw, int dtype, cudaStream_t st);
 // divide != 0: y = fold(xw) ./ count (windowed_fa, src/windowed.jl:16-19); channels = g.d

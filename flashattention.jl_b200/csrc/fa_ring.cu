@@ -99,6 +99,30 @@ int merge_t(float* oa, float* la, float* ma, const void* ob, const float* lb, co
 
 size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Exchange stream + events of one ring call, released on EVERY exit path (round 1 leaked them on an early error return).
+// On destruction the exchange stream is drained first, so no NCCL operation of this call is still in flight when
+// its buffers are reused; an NCCL group left open by an error between GroupStart and GroupEnd is closed.
+struct RingLanes {
+  cudaStream_t xs = nullptr;
+  cudaEvent_t ev[8] = {};
+  int nev = 0;
+  bool group_open = false;
+  bool done = false;           // success: the caller's stream already waits on the last exchange event, no host sync needed
+  const NcclApi* nc = nullptr;
+  int make(int n_events) {
+    FA_CUDA_TRY(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
+    for (int i = 0; i < n_events && i < 8; ++i) { FA_CUDA_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); ++nev; }
+    return FA_OK;
+  }
+  ~RingLanes() {
+    if (group_open && nc && nc->GroupEnd) nc->GroupEnd();
+    if (xs) { if (!done) cudaStreamSynchronize(xs); cudaStreamDestroy(xs); }      // destruction itself is deferred by the runtime
+    for (int i = 0; i < nev; ++i) cudaEventDestroy(ev[i]);
+  }
+};
+#define FA_NCCL_GROUP_BEGIN(L) do { FA_NCCL_TRY(nc.GroupStart()); (L).group_open = true; } while (0)
+#define FA_NCCL_GROUP_END(L) do { (L).group_open = false; FA_NCCL_TRY(nc.GroupEnd()); } while (0)
+
 // acc = (first ? 0 : acc) + part      (fp32, grid-stride)
 __global__ void accumulate_kernel(float* __restrict__ acc, const float* __restrict__ part, size_t n, int first) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -205,61 +229,58 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
   gd.mode = MODE_DENSE; gd.d = (int)d; gd.dv = (int)dv; gd.N = Nl; gd.B = B; gd.tau = 1.0f / sqrtf((float)d);
   const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(gd, dtype);
 
-  cudaStream_t cs = static_cast<cudaStream_t>(stream), xs = nullptr;
-  cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr}, ev_start = nullptr;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  RingLanes lanes;
+  lanes.nc = &nc;
   int rc = FA_OK;
   if (nranks > 1) {
-    FA_CUDA_TRY(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_compute[i], cudaEventDisableTiming));
-      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_comm[i], cudaEventDisableTiming));
-    }
-    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-    FA_CUDA_TRY(cudaEventRecord(ev_start, cs));            // inputs are ready on the caller's stream
-    FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_start, 0));
+    if ((rc = lanes.make(5))) return rc;
+    FA_CUDA_TRY(cudaEventRecord(lanes.ev[4], cs));          // inputs are ready on the caller's stream
+    FA_CUDA_TRY(cudaStreamWaitEvent(lanes.xs, lanes.ev[4], 0));
   }
+  cudaStream_t xs = lanes.xs;
+  cudaEvent_t* ev_compute = &lanes.ev[0];
+  cudaEvent_t* ev_comm = &lanes.ev[2];
   const int next = (rank + 1) % nranks, prev = (rank + nranks - 1) % nranks;
   const ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
   const void* cur_k = k;
   const void* cur_v = v;
-  for (int s = 0; s < nranks && rc == FA_OK; ++s) {
+  // tcgen05 path: the kernel merges every block after the first straight into the running (oacc, l, m) in its epilogue
+  // (FwdArgs::o_f32 = 2); the last step is followed by one conversion of oacc into `o`.  Exact-fp32 fallback: partial +
+  // merge_partials as before.
+  for (int s = 0; s < nranks; ++s) {
     const int bi = s & 1;
     if (s + 1 < nranks) {
       // exchange on the second stream: send the block we hold, receive the next one into buf[bi];
       // buf[bi] was the compute input of step s-1, so wait for that compute first.
       if (s >= 1) FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_compute[(s - 1) & 1], 0));
-      FA_NCCL_TRY(nc.GroupStart());
+      FA_NCCL_GROUP_BEGIN(lanes);
       FA_NCCL_TRY(nc.Send(cur_k, (size_t)Nl * d * B * esz, ncclUint8, next, comm, xs));
       FA_NCCL_TRY(nc.Send(cur_v, (size_t)Nl * dv * B * esz, ncclUint8, next, comm, xs));
       FA_NCCL_TRY(nc.Recv(kbuf[bi], (size_t)Nl * d * B * esz, ncclUint8, prev, comm, xs));
       FA_NCCL_TRY(nc.Recv(vbuf[bi], (size_t)Nl * dv * B * esz, ncclUint8, prev, comm, xs));
-      FA_NCCL_TRY(nc.GroupEnd());
+      FA_NCCL_GROUP_END(lanes);
       FA_CUDA_TRY(cudaEventRecord(ev_comm[bi], xs));
     }
-    // compute on the caller's stream: partial attention against the resident block, then merge
+    // compute on the caller's stream: partial attention against the resident block, merged into the running result
     if (tc) {
-      FwdArgs fa_args{q, cur_k, cur_v, oblk, nullptr, lblk, mblk, /*o_f32=*/1};
+      FwdArgs fa_args{q, cur_k, cur_v, oacc, nullptr, l, m, /*o_f32=*/s == 0 ? 1 : 2};
       set_path("tc");
-      rc = tc_fwd(gd, fa_args, dtype, cs);
+      if ((rc = tc_fwd(gd, fa_args, dtype, cs))) return rc;
+      if (s + 1 == nranks && (rc = cast_out(o, oacc, (size_t)Nl * dv * B, dtype, cs))) return rc;
     } else {
-      rc = fa_dense_fwd(q, cur_k, cur_v, oblk, lblk, mblk, Nl, d, dv, B, dtype, flags, cs);
+      if ((rc = fa_dense_fwd(q, cur_k, cur_v, oblk, lblk, mblk, Nl, d, dv, B, dtype, flags, cs))) return rc;
+      if ((rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, 0, s == 0, cs))) return rc;
     }
-    if (rc == FA_OK)
-      rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, tc ? 1 : 0, s == 0, cs);
-    if (rc == FA_OK && s + 1 < nranks) {
+    if (s + 1 < nranks) {
       FA_CUDA_TRY(cudaEventRecord(ev_compute[bi], cs));
       FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_comm[bi], 0));          // next block must have arrived
       cur_k = kbuf[bi];
       cur_v = vbuf[bi];
     }
   }
-  if (nranks > 1) {
-    // the exchange stream's work is ordered before the caller's stream (last ev_comm was waited on)
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_compute[i]); cudaEventDestroy(ev_comm[i]); }
-    cudaEventDestroy(ev_start);
-    cudaStreamDestroy(xs);       // deferred by the runtime until its work has drained
-  }
-  return rc;
+  lanes.done = true;   // the last exchange event was waited on by the caller's stream
+  return FA_OK;
 }
 
 // ------------------------------------------------------------------------------ ring backward
@@ -316,20 +337,19 @@ int fa_ring_dense_bwd(const void* q, const void* k, const void* v, const void* o
   gd.mode = MODE_DENSE; gd.d = (int)d; gd.dv = (int)dv; gd.N = Nl; gd.B = B; gd.tau = 1.0f / sqrtf((float)d);
   const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_bwd_supported(gd, dtype);
 
-  cudaStream_t cs = static_cast<cudaStream_t>(stream), xs = nullptr;
-  cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_kv[2] = {nullptr, nullptr}, ev_acc_ready = nullptr, ev_acc_recv = nullptr, ev_start = nullptr;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  RingLanes lanes;
+  lanes.nc = &nc;
   if (nranks > 1) {
-    FA_CUDA_TRY(cudaStreamCreateWithFlags(&xs, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_compute[i], cudaEventDisableTiming));
-      FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_kv[i], cudaEventDisableTiming));
-    }
-    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_acc_ready, cudaEventDisableTiming));
-    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_acc_recv, cudaEventDisableTiming));
-    FA_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-    FA_CUDA_TRY(cudaEventRecord(ev_start, cs));
-    FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_start, 0));
+    int rc0 = lanes.make(7);
+    if (rc0) return rc0;
+    FA_CUDA_TRY(cudaEventRecord(lanes.ev[6], cs));
+    FA_CUDA_TRY(cudaStreamWaitEvent(lanes.xs, lanes.ev[6], 0));
   }
+  cudaStream_t xs = lanes.xs;
+  cudaEvent_t* ev_compute = &lanes.ev[0];
+  cudaEvent_t* ev_kv = &lanes.ev[2];
+  cudaEvent_t ev_acc_ready = lanes.ev[4], ev_acc_recv = lanes.ev[5];
   const int next = (rank + 1) % nranks, prev = (rank + nranks - 1) % nranks;
   const ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
   const void* cur_k = k;
@@ -339,12 +359,12 @@ int fa_ring_dense_bwd(const void* q, const void* k, const void* v, const void* o
     const int bi = s & 1;
     if (s + 1 < nranks) {        // K/V of the next step: overlapped with this step's compute
       if (s >= 1) FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_compute[(s - 1) & 1], 0));
-      FA_NCCL_TRY(nc.GroupStart());
+      FA_NCCL_GROUP_BEGIN(lanes);
       FA_NCCL_TRY(nc.Send(cur_k, nk * esz, ncclUint8, next, comm, xs));
       FA_NCCL_TRY(nc.Send(cur_v, nv * esz, ncclUint8, next, comm, xs));
       FA_NCCL_TRY(nc.Recv(kbuf[bi], nk * esz, ncclUint8, prev, comm, xs));
       FA_NCCL_TRY(nc.Recv(vbuf[bi], nv * esz, ncclUint8, prev, comm, xs));
-      FA_NCCL_TRY(nc.GroupEnd());
+      FA_NCCL_GROUP_END(lanes);
       FA_CUDA_TRY(cudaEventRecord(ev_kv[bi], xs));
     }
     // partial gradients of (local queries) x (resident block)
@@ -362,12 +382,12 @@ int fa_ring_dense_bwd(const void* q, const void* k, const void* v, const void* o
       FA_CUDA_TRY(cudaEventRecord(ev_compute[bi], cs));
       FA_CUDA_TRY(cudaEventRecord(ev_acc_ready, cs));
       FA_CUDA_TRY(cudaStreamWaitEvent(xs, ev_acc_ready, 0));
-      FA_NCCL_TRY(nc.GroupStart());
+      FA_NCCL_GROUP_BEGIN(lanes);
       FA_NCCL_TRY(nc.Send(kacc[bi], nk * 4, ncclUint8, next, comm, xs));
       FA_NCCL_TRY(nc.Send(vacc[bi], nv * 4, ncclUint8, next, comm, xs));
       FA_NCCL_TRY(nc.Recv(kacc[bi ^ 1], nk * 4, ncclUint8, prev, comm, xs));
       FA_NCCL_TRY(nc.Recv(vacc[bi ^ 1], nv * 4, ncclUint8, prev, comm, xs));
-      FA_NCCL_TRY(nc.GroupEnd());
+      FA_NCCL_GROUP_END(lanes);
       FA_CUDA_TRY(cudaEventRecord(ev_acc_recv, xs));
       if (s + 1 < nranks) {
         FA_CUDA_TRY(cudaStreamWaitEvent(cs, ev_kv[bi], 0));
@@ -383,11 +403,7 @@ int fa_ring_dense_bwd(const void* q, const void* k, const void* v, const void* o
     if (!(rc = cast_out(dq, qacc, nk, dtype, cs)) && !(rc = cast_out(dk, kacc[fin], nk, dtype, cs)))
       rc = cast_out(dv_out, vacc[fin], nv, dtype, cs);
   }
-  if (nranks > 1) {
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_compute[i]); cudaEventDestroy(ev_kv[i]); }
-    cudaEventDestroy(ev_acc_ready); cudaEventDestroy(ev_acc_recv); cudaEventDestroy(ev_start);
-    cudaStreamDestroy(xs);
-  }
+  lanes.done = rc == FA_OK;      // success: the caller's stream waited on the last exchange event; failure: drain first
   return rc;
 }
 

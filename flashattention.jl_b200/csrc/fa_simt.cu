@@ -436,6 +436,20 @@ __global__ void fold_finalize_kernel(const Geo g, const float* __restrict__ acc,
   }
 }
 
+// slab of a larger volume (planes [plane_lo, plane_lo + nplanes) of the slowest spatial dim): y = acc ./ count with the
+// count of the WHOLE volume `g` (src/windowed.jl:16-19); acc, y :: (slab tokens, channels, B)
+template <typename T>
+__global__ void slab_divide_kernel(const Geo g, const float* __restrict__ acc, T* __restrict__ y, int channels,
+                                   long long plane_lo, long long slab_tokens) {
+  const long long total = slab_tokens * channels * g.B;
+  long long plane_tokens = 1;
+  for (int k = 0; k < g.nd - 1; ++k) plane_tokens *= g.s[k];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i % slab_tokens;
+    y[i] = from_f32<T>(acc[i] / (float)window_count_at(g, tok + plane_lo * plane_tokens));
+  }
+}
+
 template <typename T>
 __global__ void fill_uncovered_kernel(const Geo g, T* __restrict__ y, int channels) {
   const long long total = g.N * channels * g.B;
@@ -615,6 +629,15 @@ static int fill_uncovered_t(const Geo& g, void* y, int ch, cudaStream_t st) {
   fill_uncovered_kernel<T><<<ew_grid(g.N * ch * g.B), 256, 0, st>>>(g, static_cast<T*>(y), ch);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
+}
+template <typename T>
+static int slab_divide_t(const Geo& g, const float* acc, void* y, int ch, long long plane_lo, long long slab_tokens, cudaStream_t st) {
+  slab_divide_kernel<T><<<ew_grid(slab_tokens * ch * g.B), 256, 0, st>>>(g, acc, static_cast<T*>(y), ch, plane_lo, slab_tokens);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+int slab_divide(const Geo& g, const float* acc, void* y, int ch, int dtype, long long plane_lo, long long slab_tokens, cudaStream_t st) {
+  FA_DISPATCH_DTYPE(dtype, slab_divide_t<T>(g, acc, y, ch, plane_lo, slab_tokens, st));
 }
 int fill_uncovered_nan(const Geo& g, void* y, int ch, int dtype, cudaStream_t st) {
   FA_DISPATCH_DTYPE(dtype, fill_uncovered_t<T>(g, y, ch, st));

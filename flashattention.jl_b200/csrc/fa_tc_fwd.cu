@@ -768,7 +768,37 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
       tc_fence_after();
       const float inv_l = 1.f / l_run;
       const bool in_range = qi < prm.N;
-      if (prm.o_f32) {
+      if (prm.o_f32 == 2) {
+        // ring pass, steps after the first: `o`, `l`, `m` hold the running (normalised O, l, m) of the blocks seen so
+        // far; this block's partial is merged in place with the update rule of src/dense.jl:82-91 -- no separate
+        // partial buffer and merge kernel (3 extra passes over N x dv x 4 bytes per ring step in round 1)
+        float* ob = static_cast<float*>(prm.o) + (size_t)b * D * prm.N + qi;
+        float c1 = 0.f, c2 = 0.f, ln = 0.f, mn = 0.f;
+        if (in_range) {
+          const float m2 = m_true * LN2, l2 = l_run * ex2(m_used - m_true);
+          const float m1 = prm.m[(size_t)b * prm.N + qi], l1 = prm.l[(size_t)b * prm.N + qi];
+          mn = fmaxf(m1, m2);
+          const float w1 = (m1 == -INFINITY) ? 0.f : l1 * __expf(m1 - mn);
+          const float w2 = (m2 == -INFINITY) ? 0.f : l2 * __expf(m2 - mn);
+          ln = w1 + w2;
+          const float inv = ln > 0.f ? 1.f / ln : 0.f;
+          c1 = w1 * inv; c2 = w2 * inv * inv_l;
+        }
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + 32 * c, o);
+          tmem_wait_ld();
+          if (in_range) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float* po = ob + (size_t)(32 * c + e) * prm.N;
+              *po = *po * c1 + __uint_as_float(o[e]) * c2;
+            }
+          }
+        }
+        if (in_range) { prm.l[(size_t)b * prm.N + qi] = ln; prm.m[(size_t)b * prm.N + qi] = mn; }
+      } else if (prm.o_f32) {
         float* ob = static_cast<float*>(prm.o) + (size_t)b * D * prm.N + qi;
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
@@ -807,7 +837,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           }
         }
       }
-      if (in_range) {
+      if (in_range && prm.o_f32 != 2) {
         // l = sum exp(s - m_true), m = max s (natural-log domain), reference src/dense.jl:12-18
         prm.l[(size_t)b * prm.N + qi] = l_run * ex2(m_used - m_true);
         prm.m[(size_t)b * prm.N + qi] = m_true * LN2;
@@ -925,9 +955,13 @@ int tc_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   // (836 vs 670 TFLOP/s; a quarter of the exponentials on the FMA pipe); at d = 128 the pair kernel wins (1.79 vs 2.09 ms at B = 64).  FA_DENSE_BAND=0 / 2 = never / always.
   static const int dense_band = [] { const char* e = getenv("FA_DENSE_BAND"); return e ? atoi(e) : 1; }();
   if (g.mode == MODE_DENSE && !a.o_f32 && ((dense_band == 1 && g.d == 64) || dense_band == 2)) return tc_band_fwd(g, a, dtype, st);
+#ifdef FA_TRACE
+  // experiment variants (two softmax threads per row / helper warpgroup), both measured slower (profiles/r1o): only
+  // instantiated in the -DFA_TRACE build (`make trace`), not in the product library
   static const int split = [] { const char* e = getenv("FA_FWD_SPLIT"); return e ? atoi(e) : 1; }();
   if (split == 2 && g.d == 128) return fmt ? launch_tc<128, 1, 2, 2>(g, a, dtype, st) : launch_tc<128, 0, 2, 2>(g, a, dtype, st);
   if (split == 3 && g.d == 128) return fmt ? launch_tc<128, 1, 2, 3>(g, a, dtype, st) : launch_tc<128, 0, 2, 3>(g, a, dtype, st);
+#endif
   if (g.d == 128) return fmt ? launch_tc<128, 1, 2>(g, a, dtype, st) : launch_tc<128, 0, 2>(g, a, dtype, st);
   return fmt ? launch_tc<64, 1, 2>(g, a, dtype, st) : launch_tc<64, 0, 2>(g, a, dtype, st);
 }

@@ -86,6 +86,9 @@ def _load():
         "fa_windowed_slab_fwd": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp]),
         "fa_workspace_bytes_windowed_slab_bwd": (sz, [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64]),
         "fa_windowed_slab_bwd": (ci, [vp] * 9 + [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp, sz, vp]),
+        "fa_windowed_halo_plan": (ci, [ci, pi64, i64, i64, i64, ci, ci, pi64]),
+        "fa_windowed_slab_fwd_sums": (ci, [vp] * 6 + [ci, pi64, i64, i64, i64, i64, i64, i64, i64, i64, ci, ci, vp]),
+        "fa_window_divide": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_window": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_unwindow": (ci, [vp, vp, ci, pi64, i64, i64, i64, i64, i64, ci, vp]),
         "fa_softmax": (ci, [vp, vp, i64, i64, i64, ci, ci, vp]),
@@ -122,7 +125,7 @@ EXPORTED_SYMBOLS = (
     "fa_workspace_bytes_ring_dense_fwd fa_ring_dense_fwd fa_workspace_bytes_ring_dense_bwd fa_ring_dense_bwd "
     "fa_circulant2d_index fa_circulant2d_fwd fa_workspace_bytes_circulant2d_bwd fa_circulant2d_bwd "
     "fa_workspace_bytes_circulant2d_bwd_ex fa_windowed_slab_plan fa_windowed_slab_fwd fa_workspace_bytes_windowed_slab_bwd fa_windowed_slab_bwd "
-    "fa_dense_bwd_host fa_circulant_bwd_host fa_windowed_bwd_host fa_host_alloc fa_host_free fa_cast").split()
+    "fa_dense_bwd_host fa_circulant_bwd_host fa_windowed_bwd_host fa_host_alloc fa_host_free fa_cast fa_windowed_halo_plan fa_windowed_slab_fwd_sums fa_window_divide").split()
 
 
 def _check(rc: int, what: str):

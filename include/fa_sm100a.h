@@ -166,6 +166,24 @@ int fa_windowed_slab_bwd(const void* q, const void* k, const void* v, const void
                          int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
                          int dtype, int flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- windowed, ONE volume over several GPUs, OVERLAPPING windows (halo of W - stride planes in, partial-y
+ *      halo reduce out).  Window planes of the slowest spatial dim are dealt out by their start plane:
+ *      plan[6] = {own_lo, own_hi, ext_hi, win_lo, win_hi, pad_lo}.  Rank r owns planes [own_lo, own_hi) (a tiling of the
+ *      volume), computes the windows [win_lo, win_hi), which read planes [own_lo, ext_hi): its own plus ext_hi - own_hi
+ *      planes of rank r+1 (the halo the host layer fetches).  fa_windowed_slab_fwd_sums runs the windowed kernels on
+ *      that extended slab and returns the FOLD SUMS (float32, (slab_dims.., dv, B), not yet divided) and l, m of its
+ *      windows; the sums of the halo planes are sent on to rank r+1 and added there; fa_window_divide then divides the
+ *      owned planes by the window count of the WHOLE volume (src/windowed.jl:16-19; 0/0 = NaN for uncovered planes).
+ *      Together: exactly windowed_fa on the whole volume.  Forward only. */
+int fa_windowed_halo_plan(int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                          int rank, int nranks, int64_t* plan);
+int fa_windowed_slab_fwd_sums(const void* q, const void* k, const void* v, float* acc, float* l, float* m,
+                              int ndim, const int64_t* slab_dims, int64_t d, int64_t dv, int64_t B,
+                              int64_t W, int64_t stride, int64_t pad, int64_t pad_lo, int64_t nwin,
+                              int dtype, int flags, void* stream);
+int fa_window_divide(const float* acc, void* y, int ndim, const int64_t* dims, int64_t W, int64_t stride, int64_t pad,
+                     int64_t plane_lo, int64_t nplanes, int64_t channels, int64_t B, int dtype, void* stream);
+
 /* ---- standalone unfold/fold: window / unwindow (src/utils.jl:36-54) --------------------- */
 int fa_window(const void* x, void* xw, int ndim, const int64_t* dims, int64_t d, int64_t B,
               int64_t W, int64_t stride, int64_t pad, int dtype, void* stream);

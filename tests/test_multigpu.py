@@ -356,3 +356,142 @@ def test_windowed_slab_plan_random_geometries():
             first = pl.win_lo * stride - pad
             last = (pl.win_hi - 1) * stride - pad + W - 1
             assert pl.plane_lo <= max(first, 0) and min(last, spatial[-1] - 1) < pl.plane_hi
+
+
+# ------------------------------------------------------------------------------------------------ halo splits
+def test_windowed_halo_plan_tiles_volume_and_covers_windows():
+    """fa_windowed_halo_plan (host, integer): owned planes tile the volume, window ranges tile the windows, and every
+    window of a rank reads only planes [own_lo, ext_hi) with pad_lo zero planes in front -- against the definition."""
+    import fa_sm100a as fa
+    from fa_sm100a import halo
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        S = int(rng.integers(8, 200)); W = int(rng.integers(1, 12)); stride = int(rng.integers(1, W + 3)); pad = int(rng.integers(0, W))
+        G = int(rng.integers(1, 9))
+        if S + 2 * pad < W:
+            continue
+        nw = (S + 2 * pad - W) // stride + 1
+        plans = [halo.windowed_halo_plan((S,), W, stride, pad, r, G) for r in range(G)]
+        assert plans[0].own_lo == 0 and plans[-1].own_hi == S and plans[0].win_lo == 0 and plans[-1].win_hi == nw
+        for a, b in zip(plans, plans[1:]):
+            assert a.own_hi == b.own_lo and a.win_hi == b.win_lo
+        for pl in plans:
+            assert pl.own_lo <= pl.own_hi <= pl.ext_hi <= S
+            for w in range(pl.win_lo, pl.win_hi):
+                lo, hi = w * stride - pad, w * stride - pad + W          # planes the window reads (outside [0, S): padding)
+                assert max(lo, 0) >= pl.own_lo
+                assert min(hi, S) <= pl.ext_hi
+                assert lo - (pl.win_lo * stride - pad) == (w - pl.win_lo) * stride
+            if pl.nwin:
+                assert pl.pad_lo == pl.own_lo - (pl.win_lo * stride - pad) and pl.pad_lo >= 0
+
+
+def test_local_comm_is_a_ring():
+    from fa_sm100a.halo import LocalComm
+    def fn(c):
+        a, b = c.exchange(torch.tensor([c.rank * 10.0]), torch.tensor([c.rank * 10.0 + 1]), torch.zeros(1), torch.zeros(1))
+        return float(a), float(b)
+    out = LocalComm(4).run(fn)
+    assert out == [(31.0, 10.0), (1.0, 20.0), (11.0, 30.0), (21.0, 0.0)]      # (prev's to_next, next's to_prev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,N,d,W,G", [(torch.bfloat16, 1024, 64, 255, 4), (torch.bfloat16, 512, 64, 64, 2), (torch.float32, 240, 16, 9, 3),
+                                           (torch.float16, 768, 128, 33, 3)])
+def test_circulant_halo_split_equals_whole_sequence(dtype, N, d, W, G):
+    """One periodic-band sequence sharded by tokens over G ranks (all ranks emulated in this process, LocalComm): every
+    rank's (O, l, m) and (dq, dk, dv) against the unsharded call / the oracle; the halo exchange is the only coupling."""
+    import fa_sm100a as fa
+    from fa_sm100a import halo
+    q, k, v, g = (randn_np((N, d, 2), s, dtype) for s in range(4))
+    Nl = N // G
+    sh = lambda t, r: to_dev(np.asfortranarray(t[r * Nl:(r + 1) * Nl]), dtype)
+
+    def rank_fn(c):
+        r = c.rank
+        O, l, m, ctx = halo.circulant_fa_halo(sh(q, r), sh(k, r), sh(v, r), W, c)
+        grads = halo.circulant_fa_halo_backward(ctx, sh(g, r), W, c)
+        return tuple(to_np(t) for t in (O, l, m) + tuple(grads))
+    outs = halo.LocalComm(G).run(rank_fn)
+    cat = lambda i: np.concatenate([o[i] for o in outs])
+    O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (q, k, v)), W)
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert rel_err(cat(0), O0, dtype) < tol and rel_err(cat(1), l0) < tol and np.abs(cat(2) - m0).max() < tol * max(1.0, np.abs(m0).max())
+    want = fo.circulant_backward_given(*(t.astype(np.float64) for t in (q, k, v)), cat(0), g.astype(np.float64), cat(1), cat(2), W)
+    for i, w in zip((3, 4, 5), want):
+        assert rel_err(cat(i), w, dtype) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spatial,W,stride,pad,G,d,dtype", [
+    ((64,), 16, 4, 0, 3, 64, torch.bfloat16),              # 1-D, heavy overlap
+    ((4096,), 64, 16, 0, 4, 64, torch.bfloat16),           # logs/compare1.txt windowed geometry (stride 16)
+    ((16, 24), 3, 1, 1, 4, 64, torch.float16),             # 2-D sliding windows, padding on both sides
+    ((12, 10, 20), 5, 2, 2, 3, 64, torch.bfloat16),        # 3-D overlapping
+    ((20, 30), 7, 7, 3, 2, 16, torch.float32),             # exact cover goes through the same path (no halo needed)
+    ((9, 40), 4, 3, 0, 5, 8, torch.float32),               # uncovered tail planes -> NaN
+])
+def test_windowed_halo_split_equals_whole_volume(spatial, W, stride, pad, G, d, dtype):
+    """One volume with OVERLAPPING windows over G ranks (emulated in-process): y of every rank's planes and (l, m) of its
+    windows against windowed_fa on the whole volume (oracle), NaN pattern included."""
+    import fa_sm100a as fa
+    from fa_sm100a import halo
+    q, k, v = (randn_np(spatial + (d, 2), s, dtype) for s in range(3))
+    ax = len(spatial) - 1
+    plans = [halo.windowed_halo_plan(spatial, W, stride, pad, r, G) for r in range(G)]
+
+    def rank_fn(c):
+        pl = plans[c.rank]
+        cut = lambda t: to_dev(np.asfortranarray(np.take(t, range(pl.own_lo, pl.own_hi), axis=ax)), dtype)
+        y, l, m = halo.windowed_fa_halo(cut(q), cut(k), cut(v), spatial, W, c, stride, pad)
+        return to_np(y), to_np(l), to_np(m)
+    outs = halo.LocalComm(G).run(rank_fn)
+    y = np.concatenate([o[0] for o in outs], axis=ax)
+    l = np.concatenate([o[1] for o in outs], axis=2)
+    m = np.concatenate([o[2] for o in outs], axis=2)
+    y0, l0, m0 = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), W, stride, pad)
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert y.shape == y0.shape and l.shape == l0.shape
+    assert rel_err(y, y0, dtype) < tol and rel_err(l, l0) < max(tol, 1e-5) and rel_err(m, m0) < max(tol, 1e-5)
+
+
+def _nccl_halo_worker(rank, world, port, q, k, v, g, W, out):
+    sys.path.insert(0, os.path.join(ROOT, "flashattention.jl_b200"))
+    import fa_sm100a as fa
+    from fa_sm100a import halo
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    comm = halo.DistComm()
+    dt = torch.bfloat16
+    n = q.shape[0] // world
+    sh = lambda t: fa.jl_array(np.asfortranarray(t[rank * n:(rank + 1) * n]), dtype=dt, device=f"cuda:{rank}")
+    O, l, m, ctx = halo.circulant_fa_halo(sh(q), sh(k), sh(v), W, comm)
+    grads = halo.circulant_fa_halo_backward(ctx, sh(g), W, comm)
+    # windowed: a 1-D sequence with overlapping windows, planes = tokens
+    pl = halo.windowed_halo_plan((q.shape[0],), 64, 16, 0, rank, world)
+    cut = lambda t: fa.jl_array(np.asfortranarray(t[pl.own_lo:pl.own_hi]), dtype=dt, device=f"cuda:{rank}")
+    yw, lw, mw = halo.windowed_fa_halo(cut(q), cut(k), cut(v), (q.shape[0],), 64, comm, 16, 0)
+    out[rank] = tuple(t.float().cpu() for t in (O, l, m) + tuple(grads) + (yw, lw))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_halo_splits_two_ranks_nccl():
+    """The two halo splits with REAL NCCL point-to-point exchanges between two GPUs."""
+    N, d, W = 2048, 64, 255
+    q, k, v, g = (randn_np((N, d, 2), s, torch.bfloat16) for s in range(4))
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_nccl_halo_worker, args=(world, port, q, k, v, g, W, out), nprocs=world, join=True)
+    cat = lambda i, ax=0: np.concatenate([out[r][i].numpy().astype(np.float64) for r in range(world)], axis=ax)
+    O0, l0, m0 = fo.circulant_fa(*(t.astype(np.float64) for t in (q, k, v)), W)
+    assert rel_err(cat(0), O0, torch.bfloat16) < 2e-3 and rel_err(cat(1), l0) < 2e-3
+    want = fo.circulant_backward_given(*(t.astype(np.float64) for t in (q, k, v)), cat(0), g.astype(np.float64), cat(1), cat(2), W)
+    for i, w in zip((3, 4, 5), want):
+        assert rel_err(cat(i), w, torch.bfloat16) < 2e-3
+    y0, lw0, _ = fo.windowed_fa(*(t.astype(np.float64) for t in (q, k, v)), 64, 16, 0)
+    assert rel_err(cat(6), y0, torch.bfloat16) < 2e-3 and rel_err(cat(7, 2), lw0) < 2e-3
