@@ -12,6 +12,7 @@
 // communicator was created with (torch's bundled one), so the library still loads without NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -245,9 +246,14 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
   const ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
   const void* cur_k = k;
   const void* cur_v = v;
-  // tcgen05 path: the kernel merges every block after the first straight into the running (oacc, l, m) in its epilogue
-  // (FwdArgs::o_f32 = 2); the last step is followed by one conversion of oacc into `o`.  Exact-fp32 fallback: partial +
-  // merge_partials as before.
+  // Two ways to fold a block's partial into the running (oacc, l, m) on the tcgen05 path:
+  //   FA_RING_FUSED=1: the forward kernel merges in its epilogue (FwdArgs::o_f32 = 2): no partial buffer, no merge pass;
+  //   default:         float32 partial + merge_partials_kernel.
+  // Measured on 2 x B200 (2 x 16384 tokens, d = 128, 8 heads; profiles/r2h_ring.md): fused 2.44 ms, unfused 2.32 ms.  The
+  // pair kernel runs one CTA per SM, so the read-modify-write of oacc sits on each CTA's critical path, while the
+  // separate merge is a full-bandwidth streaming pass (0.04 ms): fusing removes 3 passes over N x dv x 4 bytes but
+  // costs more than it saves, hence opt-in.
+  static const int fused = [] { const char* e = getenv("FA_RING_FUSED"); return e ? atoi(e) : 0; }();
   for (int s = 0; s < nranks; ++s) {
     const int bi = s & 1;
     if (s + 1 < nranks) {
@@ -263,11 +269,16 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
       FA_CUDA_TRY(cudaEventRecord(ev_comm[bi], xs));
     }
     // compute on the caller's stream: partial attention against the resident block, merged into the running result
-    if (tc) {
+    if (tc && fused) {
       FwdArgs fa_args{q, cur_k, cur_v, oacc, nullptr, l, m, /*o_f32=*/s == 0 ? 1 : 2};
       set_path("tc");
       if ((rc = tc_fwd(gd, fa_args, dtype, cs))) return rc;
       if (s + 1 == nranks && (rc = cast_out(o, oacc, (size_t)Nl * dv * B, dtype, cs))) return rc;
+    } else if (tc) {
+      FwdArgs fa_args{q, cur_k, cur_v, oblk, nullptr, lblk, mblk, /*o_f32=*/1};
+      set_path("tc");
+      if ((rc = tc_fwd(gd, fa_args, dtype, cs))) return rc;
+      if ((rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, 1, s == 0, cs))) return rc;
     } else {
       if ((rc = fa_dense_fwd(q, cur_k, cur_v, oblk, lblk, mblk, Nl, d, dv, B, dtype, flags, cs))) return rc;
       if ((rc = merge_partials(oacc, l, m, oblk, lblk, mblk, s + 1 == nranks ? o : nullptr, Nl, (int)dv, B, dtype, 0, s == 0, cs))) return rc;

@@ -7,7 +7,7 @@
 #include "fa_ptx.cuh"
 
 namespace fa {
-int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B);
+int make_tmap_public(CUtensorMap* tm, const void* base, int dtype, long long N, int D, long long B, long long stride_c = 0, long long stride_b = 0);
 
 namespace {
 using namespace ptx;

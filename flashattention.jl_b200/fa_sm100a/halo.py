@@ -44,12 +44,14 @@ class DistComm:
             ops.append(d.P2POp(d.isend, to_prev.contiguous(), prev, self.group))
         if to_next is not None:
             ops.append(d.P2POp(d.isend, to_next.contiguous(), nxt, self.group))
-        if from_prev_like is not None:
-            rp = torch.empty_like(from_prev_like, memory_format=torch.contiguous_format)
-            ops.append(d.P2POp(d.irecv, rp, prev, self.group))
+        # receives are posted in the order the PEER sends (to_prev first, to_next second): with two ranks prev == next and
+        # messages between one pair of ranks match in posting order -- my next's `to_prev` is my `from_next`
         if from_next_like is not None:
             rn = torch.empty_like(from_next_like, memory_format=torch.contiguous_format)
             ops.append(d.P2POp(d.irecv, rn, nxt, self.group))
+        if from_prev_like is not None:
+            rp = torch.empty_like(from_prev_like, memory_format=torch.contiguous_format)
+            ops.append(d.P2POp(d.irecv, rp, prev, self.group))
         for w in (d.batch_isend_irecv(ops) if ops else []):
             w.wait()
         return rp, rn
