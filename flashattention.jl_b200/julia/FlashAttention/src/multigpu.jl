@@ -26,13 +26,15 @@ function ring_dense_fa(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T, 3}, com
     m = statarray(q, Nl, 1, batchsize)
     nws = ccall(sym(:fa_workspace_bytes_ring_dense_fwd), Csize_t, (Int64, Int64, Int64, Int64, Cint),
                 Nl, d, dv, batchsize, fa_dtype(T))
-    ws = CuArray{UInt8}(undef, max(nws, 256))
-    rc = ccall(sym(:fa_ring_dense_fwd), Cint,
-               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-                Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
-               devptr(q), devptr(k), devptr(v), devptr(O), devptr(l), devptr(m),
-               Nl, d, dv, batchsize, fa_dtype(T), Cint(flags), comm, Cint(rank), Cint(nranks),
-               devptr(ws), length(ws), current_stream())
+    ws = workspace(nws)
+    rc = GC.@preserve O k l m q v ws begin
+        ccall(sym(:fa_ring_dense_fwd), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                    Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                   devptr(q), devptr(k), devptr(v), devptr(O), devptr(l), devptr(m),
+                   Nl, d, dv, batchsize, fa_dtype(T), Cint(flags), comm, Cint(rank), Cint(nranks),
+                   devptr(ws), length(ws), current_stream())
+    end
     check(rc, "fa_ring_dense_fwd")
     CUDA.synchronize()          # the workspace must outlive the enqueued work
     return O, l, m
@@ -56,14 +58,16 @@ function ring_dense_fa_backward(q::CuArray{T, 3}, k::CuArray{T, 3}, v::CuArray{T
     dQ, dK, dV = similar(q), similar(k), similar(v)
     nws = ccall(sym(:fa_workspace_bytes_ring_dense_bwd), Csize_t, (Int64, Int64, Int64, Int64, Cint, Cint),
                 Nl, d, dv, batchsize, fa_dtype(T), Cint(flags))
-    ws = CuArray{UInt8}(undef, max(nws, 256))
-    rc = ccall(sym(:fa_ring_dense_bwd), Cint,
-               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-                Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cint, Cint,
-                Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
-               devptr(q), devptr(k), devptr(v), devptr(O), devptr(dO), devptr(l), devptr(m),
-               devptr(dQ), devptr(dK), devptr(dV), Nl, d, dv, batchsize, fa_dtype(T), Cint(flags),
-               comm, Cint(rank), Cint(nranks), devptr(ws), length(ws), current_stream())
+    ws = workspace(nws)
+    rc = GC.@preserve O dK dO dQ dV k l m q v ws begin
+        ccall(sym(:fa_ring_dense_bwd), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                    Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cint, Cint,
+                    Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                   devptr(q), devptr(k), devptr(v), devptr(O), devptr(dO), devptr(l), devptr(m),
+                   devptr(dQ), devptr(dK), devptr(dV), Nl, d, dv, batchsize, fa_dtype(T), Cint(flags),
+                   comm, Cint(rank), Cint(nranks), devptr(ws), length(ws), current_stream())
+    end
     check(rc, "fa_ring_dense_bwd")
     CUDA.synchronize()
     return dQ, dK, dV
@@ -111,11 +115,13 @@ function windowed_fa_slab(q::CuArray{T, N}, k::CuArray{T, N}, v::CuArray{T, N}, 
     y = similar(q, size(q)[1:D]..., dv, B)
     l = CUDA.zeros(Float32, WD, 1, L, B)
     m = CUDA.zeros(Float32, WD, 1, L, B)
-    rc = ccall(sym(:fa_windowed_slab_fwd), Cint,
-               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-                Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}),
-               devptr(q), devptr(k), devptr(v), devptr(y), devptr(l), devptr(m),
-               D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw, fa_dtype(T), Cint(flags), current_stream())
+    rc = GC.@preserve k l m q v y begin
+        ccall(sym(:fa_windowed_slab_fwd), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                    Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}),
+                   devptr(q), devptr(k), devptr(v), devptr(y), devptr(l), devptr(m),
+                   D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw, fa_dtype(T), Cint(flags), current_stream())
+    end
     check(rc, "fa_windowed_slab_fwd")
     return y, l, m
 end
@@ -131,13 +137,27 @@ function windowed_fa_slab_backward(q::CuArray{T, N}, k::CuArray{T, N}, v::CuArra
     nws = ccall(sym(:fa_workspace_bytes_windowed_slab_bwd), Csize_t,
                 (Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64),
                 D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw)
-    ws = CuArray{UInt8}(undef, max(nws, 256))
-    rc = ccall(sym(:fa_windowed_slab_bwd), Cint,
-               (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-                Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
-               devptr(q), devptr(k), devptr(v), devptr(dy), devptr(l), devptr(m), devptr(dq), devptr(dk), devptr(dvv),
-               D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw, fa_dtype(T), Cint(flags),
-               devptr(ws), length(ws), current_stream())
+    ws = workspace(nws)
+    rc = GC.@preserve dk dq dvv dy k l m q v ws begin
+        ccall(sym(:fa_windowed_slab_bwd), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                    Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                   devptr(q), devptr(k), devptr(v), devptr(dy), devptr(l), devptr(m), devptr(dq), devptr(dk), devptr(dvv),
+                   D, dims, d, dv, B, windowsize, stride, pad, plan.pad_lo, nw, fa_dtype(T), Cint(flags),
+                   devptr(ws), length(ws), current_stream())
+    end
     check(rc, "fa_windowed_slab_bwd")
     return dq, dk, dvv
+end
+
+# ---- halo splits (SURVEY 8e): the neighbour exchanges are the caller's (NCCL.jl Send/Recv of plane ranges); the library
+# supplies the plan, the un-normalised slab forward and the final division -- see fa_sm100a/halo.py for the complete
+# sequence of calls (exchange q/k/v halo planes in, fa_windowed_slab_fwd_sums, exchange partial sums out, fa_window_divide)
+"`(own_lo, own_hi, ext_hi, win_lo, win_hi, pad_lo)` (0-based, half-open) of rank `rank` for ONE volume with overlapping windows."
+function windowed_halo_plan(dims::Vector{Int64}, windowsize::Integer, stride::Integer, pad::Integer, rank::Integer, nranks::Integer)
+    plan = zeros(Int64, 6)
+    rc = ccall(sym(:fa_windowed_halo_plan), Cint, (Cint, Ptr{Int64}, Int64, Int64, Int64, Cint, Cint, Ptr{Int64}),
+               length(dims), dims, windowsize, stride, pad, rank, nranks, plan)
+    check(rc, "fa_windowed_halo_plan")
+    return Tuple(plan)
 end

@@ -35,8 +35,10 @@ function window(x::CuArray{T, N}, windowsize; stride=windowsize, pad=(windowsize
     d, B = size(x, N-1), size(x, N)
     L = prod((dims[i] + 2pad - windowsize) ÷ stride + 1 for i in 1:D)
     X = similar(x, windowsize^D, d, L, B)
-    rc = ccall(sym(:fa_window), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cvoid}),
-               devptr(x), devptr(X), D, dims, d, B, windowsize, stride, pad, fa_dtype(T), current_stream())
+    rc = GC.@preserve X x begin
+        ccall(sym(:fa_window), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cvoid}),
+                   devptr(x), devptr(X), D, dims, d, B, windowsize, stride, pad, fa_dtype(T), current_stream())
+    end
     check(rc, "fa_window")
     return X
 end
@@ -46,8 +48,10 @@ function unwindow(X::CuArray{T, N2}, outputsize::NTuple{N}, windowsize; stride=w
     dims = Int64[outputsize[i] for i in 1:D]
     d, B = outputsize[N-1], outputsize[N]
     x = similar(X, outputsize...)
-    rc = ccall(sym(:fa_unwindow), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cvoid}),
-               devptr(X), devptr(x), D, dims, d, B, windowsize, stride, pad, fa_dtype(T), current_stream())
+    rc = GC.@preserve X x begin
+        ccall(sym(:fa_unwindow), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int64}, Int64, Int64, Int64, Int64, Int64, Cint, Ptr{Cvoid}),
+                   devptr(X), devptr(x), D, dims, d, B, windowsize, stride, pad, fa_dtype(T), current_stream())
+    end
     check(rc, "fa_unwindow")
     return x
 end
