@@ -1080,6 +1080,7 @@ bool tc_win_supported(const Geo& g, int dtype) {
 
 bool tc_winx_supported(const Geo& g, const FwdArgs& a, int dtype);
 int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st);
+int tc_winx_groups_per_window_row(const Geo& g);
 
 int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   if (!tc_win_supported(g, dtype)) { set_error("tc_win_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
@@ -1094,9 +1095,8 @@ int tc_win_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      const int nwc = 4 * (128 / g.WD);
-      const long long groups = (long long)((g.o[0] + nwc - 1) / nwc) * g.o[1] * g.o[2] * g.B;
-      if (winx == 1 || (g.nd == 3 && groups >= 4LL * sms)) return tc_winx_fwd(g, a, dtype, st);
+      const long long groups = (long long)tc_winx_groups_per_window_row(g) * g.o[1] * g.o[2] * g.B;
+      if (winx == 1 || (g.nd == 3 && groups >= 8LL * sms)) return tc_winx_fwd(g, a, dtype, st);
     }
   }
   if (g.d == 128) return fmt ? launch_win_fwd<128, 1, 1>(g, a, st) : launch_win_fwd<128, 1, 0>(g, a, st);

@@ -67,9 +67,12 @@ __device__ __forceinline__ void tma_prefetch_5d(const void* tmap, int c0, int c1
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-struct XCfg {
+// NTILES = 4: one CTA per SM, four 128-row tiles = all 512 TMEM columns, 40-byte output runs (config 5: groups of four
+// windows).  NTILES = 2: two CTAs per SM with two tiles each -- smaller boxes and 20-byte runs, but the two CTAs' phases
+// (TMA stream + repack | softmax | output) overlap each other, which one CTA's phases cannot.
+template <int NTILES> struct XCfg {
   static constexpr int D = 64;
-  static constexpr int NT = 4;                               // 128-row tiles per CTA = all 512 TMEM columns
+  static constexpr int NT = NTILES;                          // 128-row tiles per CTA
   static constexpr int CONSUMERS = 128 * NT;                 // warps 0..15: repack / softmax / output (thread == tile row)
   static constexpr int THREADS = CONSUMERS + 32;             // warp 16: TMA producer
   static constexpr int CH = 16;                              // channels per TMA box = one tcgen05.mma K step
@@ -79,14 +82,16 @@ struct XCfg {
   static constexpr int TILE_BYTES = 2 * BOX_BYTES;           // 16 KB
   static constexpr int OFF_TQ = 0;                           // [NT] Q tiles, later V tiles
   static constexpr int OFF_TK = NT * TILE_BYTES;             // [NT] K tiles, later the output staging
-  static constexpr int NSLOT = 3;
-  static constexpr int SLOT_BYTES = 25600;                   // >= BX * RG * CH * 2
+  static constexpr int NSLOT = NT == 4 ? 3 : 2;
+  static constexpr int SLOT_BYTES = NT == 4 ? 25600 : 19200; // >= BX * RG * CH * 2
+  static constexpr int CTAS_PER_SM = NT == 4 ? 1 : 2;
+  static constexpr int TMEM_COLS = 128 * NT;
   static constexpr int OFF_ST = 2 * NT * TILE_BYTES;
   static constexpr int OFF_ROWTAB = OFF_ST + NSLOT * SLOT_BYTES;   // uint32[128]: static (rowidx << 16 | column) of a tile row
   static constexpr int OFF_ROWOFF = OFF_ROWTAB + 128 * 4;          // int[64]: global token offset of every (y, z) row of the group, -1 = padding
   static constexpr int OFF_BAR = OFF_ROWOFF + 64 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory budget");
 };
 
 struct XParams {
@@ -140,13 +145,13 @@ __device__ __forceinline__ GroupInfo decode_group(const XParams& prm, unsigned g
   return gi;
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(XCfg::THREADS, 1)
+template <int FMT, int NTILES>
+__global__ void __launch_bounds__(XCfg<NTILES>::THREADS, XCfg<NTILES>::CTAS_PER_SM)
 tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_constant__ CUtensorMap tk_s,
                    const __grid_constant__ CUtensorMap tv_s, const __grid_constant__ CUtensorMap tq_l,
                    const __grid_constant__ CUtensorMap tk_l, const __grid_constant__ CUtensorMap tv_l,
                    const XParams prm) {
-  using C = XCfg;
+  using C = XCfg<NTILES>;
   using T = typename El<FMT>::type;
   constexpr int D = C::D;
   extern __shared__ uint8_t smem_raw[];
@@ -179,7 +184,7 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
     }
     rowtab[r] = e;
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -236,9 +241,10 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
   // of tile rp_t.  Lane bits = (c0, c1, j2, t0, t1): the 8 lanes of a quarter warp store to 8 different 16-byte bank
   // groups ((j ^ c) & 7 distinct) and the 32 two-byte loads of a warp spread over the four windows of the group --
   // 2.2 wavefronts per load instead of 6.5 with lanes along j (64-byte staging rows alias to two bank groups).
-  const int rp_t = (lane >> 3) & 3;
-  const int rp_j = (warp & 3) | (((lane >> 2) & 1) << 2) | (((warp >> 2) & 1) << 3);
-  const int rp_c = (lane & 3) | (((warp >> 3) & 1) << 2);
+  // (two tiles: lane bits = (c0, c1, c2, j2, t0), warp bits = (j0, j1, j3): 2.0 wavefronts per load)
+  const int rp_t = C::NT == 4 ? (lane >> 3) & 3 : lane >> 4;
+  const int rp_j = (warp & 3) | ((C::NT == 4 ? (lane >> 2) & 1 : (lane >> 3) & 1) << 2) | (((warp >> 2) & 1) << 3);
+  const int rp_c = C::NT == 4 ? (lane & 3) | (((warp >> 3) & 1) << 2) : lane & 7;
   constexpr uint32_t idesc_qk = make_idesc_f16(FMT, FMT, 1, 1, 128, 128);
   constexpr uint32_t idesc_pv = make_idesc_f16(FMT, FMT, 0, 0, 128, D);
   const float2 scale2 = make_float2(prm.scale_log2, prm.scale_log2);
@@ -493,12 +499,12 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
 
   tc_fence_before();
   __syncthreads();                                         // all 17 warps (the producer arrives from its own branch)
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int FMT>
+template <int FMT, int NTILES>
 int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
-  using C = XCfg;
+  using C = XCfg<NTILES>;
   const int dtype = FMT ? FA_BF16 : FA_F16;
   CUtensorMap tm[6];
   memset(tm, 0, sizeof(tm));
@@ -509,12 +515,13 @@ int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
     if ((rc = make_win_tmap_box(&tm[x], src[x], dtype, g, C::D, prm.BXs, by, bz, C::CH))) return rc;
     if ((rc = make_win_tmap_box(&tm[3 + x], src[x], dtype, g, C::D, prm.BXl, by, bz, C::CH))) return rc;
   }
-  auto kern = tc_winx_fwd_kernel<FMT>;
+  auto kern = tc_winx_fwd_kernel<FMT, NTILES>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(prm.ngroups < sms ? prm.ngroups : sms);
+  const long long cap = (long long)sms * C::CTAS_PER_SM;
+  const unsigned grid = (unsigned)(prm.ngroups < cap ? prm.ngroups : cap);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
@@ -524,30 +531,36 @@ int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
 
 // Does the streamed kernel take this call?  Exact-cover windows (stride == W), d = dv = 64, 16-bit, TMA-legal rows
 // (x extent a multiple of 8 tokens, 16-byte aligned bases), no fold accumulator, boxes that fit a staging slot.
+template <int NTILES>
+static bool winx_geo_ok(const Geo& g) {
+  using C = XCfg<NTILES>;
+  const int G = 128 / g.WD, nwc = C::NT * G, TW = nwc * g.W, RG = g.WD / g.W;
+  const int BXl = (TW + 7 + 7) / 8 * 8;
+  if (RG > 64 || BXl > 256 || (long long)BXl * RG * C::CH * 2 > C::SLOT_BYTES) return false;   // TMA box extents <= 256
+  if ((long long)C::D * RG * (TW + 2) * 2 > 2LL * C::NT * C::TILE_BYTES) return false;      // output staging over the V and K tiles
+  if ((long long)((g.o[0] + nwc - 1) / nwc) * g.o[1] * g.o[2] * g.B > 0x7fffffffLL) return false;      // 32-bit group index
+  return true;
+}
+int winx_tiles() { static const int nt = [] { const char* e = getenv("FA_WINX_NT"); const int v = e ? atoi(e) : 4; return v == 2 ? 2 : 4; }(); return nt; }
+
 bool tc_winx_supported(const Geo& g, const FwdArgs& a, int dtype) {
-  using C = XCfg;
   if (dtype != FA_BF16 && dtype != FA_F16) return false;
   if (g.mode != MODE_WINDOWED || g.d != 64 || g.dv != 64 || a.acc) return false;
   if (g.stride != g.W || g.s[0] % 8 != 0 || g.WD > 128 || g.WD < 1) return false;
   if ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v)) & 15) return false;
   if (reinterpret_cast<uintptr_t>(a.o) & 3) return false;
   if ((g.N & 1) || g.N * 64 > 0x7fffffffLL || g.padv[0] > 1000) return false;
-  if ((long long)((g.o[0] + 3) / 4 + 1) * g.o[1] * g.o[2] * g.B > 0x7fffffffLL) return false;      // 32-bit group index
-  const int G = 128 / g.WD, nwc = C::NT * G, TW = nwc * g.W, RG = g.WD / g.W;
-  const int BXl = (TW + 7 + 7) / 8 * 8;
-  if (RG > 64 || BXl > 256 || (long long)BXl * RG * C::CH * 2 > C::SLOT_BYTES) return false;   // TMA box extents <= 256
-  if ((long long)C::D * RG * (TW + 2) * 2 > 2LL * C::NT * C::TILE_BYTES) return false;      // output staging over the V and K tiles
-  return true;
+  return winx_tiles() == 4 ? winx_geo_ok<4>(g) : winx_geo_ok<2>(g);
 }
 
 int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
-  using C = XCfg;
   if (!tc_winx_supported(g, a, dtype)) { set_error("tc_winx_fwd: unsupported configuration"); return FA_ERR_UNSUPPORTED; }
+  const int NT = winx_tiles();
   XParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.q = a.q; prm.k = a.k; prm.v = a.v; prm.y = a.o; prm.l = a.l; prm.m = a.m;
   prm.g = g;
-  prm.G = 128 / g.WD; prm.nwc = C::NT * prm.G; prm.TW = prm.nwc * g.W; prm.RG = g.WD / g.W;
+  prm.G = 128 / g.WD; prm.nwc = NT * prm.G; prm.TW = prm.nwc * g.W; prm.RG = g.WD / g.W;
   prm.gpr = (g.o[0] + prm.nwc - 1) / prm.nwc;
   prm.BXs = (prm.TW + 7) / 8 * 8;
   prm.BXl = (prm.TW + 7 + 7) / 8 * 8;
@@ -563,7 +576,10 @@ int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   { const char* e = getenv("FA_WINX_DBG"); prm.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
 #endif
-  return dtype == FA_BF16 ? launch_winx<1>(g, a, prm, st) : launch_winx<0>(g, a, prm, st);
+  if (NT == 4) return dtype == FA_BF16 ? launch_winx<1, 4>(g, a, prm, st) : launch_winx<0, 4>(g, a, prm, st);
+  return dtype == FA_BF16 ? launch_winx<1, 2>(g, a, prm, st) : launch_winx<0, 2>(g, a, prm, st);
 }
+
+int tc_winx_groups_per_window_row(const Geo& g) { const int nwc = winx_tiles() * (128 / g.WD); return (g.o[0] + nwc - 1) / nwc; }
 
 }  // namespace fa
