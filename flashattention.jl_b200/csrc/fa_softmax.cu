@@ -1,6 +1,7 @@
 // fa_softmax.cu -- standalone safe softmax along Julia dim 1 (columns, contiguous) or dim 2
 // (rows, strided) of a column-major (M, N, B) array.  Replaces fused_softmax! / col_softmax! /
-// row_softmax! (reference src/fused_softmax.jl:11-39).  HBM-bound: two reads + one write.
+// row_softmax! (reference src/fused_softmax.jl:11-39).  HBM-bound: one read + one write when a column fits the
+// registers of its thread group (dim 1, M up to 32768 Float32), two reads + one write otherwise.
 #include "fa_common.cuh"
 
 namespace fa {
@@ -93,10 +94,97 @@ __global__ void softmax_dim2_sliced_kernel(T* __restrict__ out, const T* __restr
   }
 }
 
+// dim 1, column held in REGISTERS: G threads per column (a warp, 256 or 1024 threads), each thread keeps up to 8 16-byte
+// vectors of the column -- one read and one write of the array (the two-pass kernels above read it twice).  Covers
+// the reference's logged column-softmax shapes (logs/sm_cuda.txt: M = 256 .. 8192, Float32).
+template <typename T, int G>
+__global__ void __launch_bounds__(G >= 256 ? G : 256)
+softmax_dim1_cached_kernel(T* __restrict__ out, const T* __restrict__ in, long long M, long long cols) {
+  constexpr int EPV = 16 / (int)sizeof(T);              // elements per 16-byte vector
+  constexpr int CPB = G >= 256 ? 1 : 256 / G;           // columns per block
+  __shared__ float smx[32], ssum[32];
+  const int t = threadIdx.x % G, sub = threadIdx.x / G;
+  const long long nvec = M / EPV;
+  for (long long col = (long long)blockIdx.x * CPB + sub; col < cols; col += (long long)gridDim.x * CPB) {
+    const uint4* x = reinterpret_cast<const uint4*>(in + col * M);
+    uint4* y = reinterpret_cast<uint4*>(out + col * M);
+    uint4 v[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = t + (long long)k * G;
+      if (i < nvec) {
+        v[k] = x[i];
+        const T* e = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) mx = fmaxf(mx, to_f32<T>(e[j]));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (G > 32) {
+      if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+      __syncthreads();
+      mx = -INFINITY;
+      for (int w = 0; w < G / 32; ++w) mx = fmaxf(mx, smx[w]);
+    }
+    float sum = 0.f;                                     // (the exponentials are recomputed below instead of kept: registers)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = t + (long long)k * G;
+      if (i < nvec) {
+        const T* e = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) sum += expf(to_f32<T>(e[j]) - mx);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (G > 32) {
+      if ((threadIdx.x & 31) == 0) ssum[threadIdx.x >> 5] = sum;
+      __syncthreads();
+      sum = 0.f;
+      for (int w = 0; w < G / 32; ++w) sum += ssum[w];
+      __syncthreads();                                   // smx / ssum are reused by the next column of this block
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = t + (long long)k * G;
+      if (i < nvec) {
+        uint4 o4;
+        T* e = reinterpret_cast<T*>(&o4);
+        const T* xi = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) e[j] = from_f32<T>(expf(to_f32<T>(xi[j]) - mx) * inv);
+        y[i] = o4;
+      }
+    }
+  }
+}
+
+template <typename T, int G>
+static int launch_cached(void* out, const void* in, long long M, long long cols, cudaStream_t st) {
+  constexpr int CPB = G >= 256 ? 1 : 256 / G;
+  long long blocks = (cols + CPB - 1) / CPB;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  softmax_dim1_cached_kernel<T, G><<<(unsigned)blocks, G >= 256 ? G : 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M, cols);
+  FA_CUDA_TRY(cudaGetLastError());
+  return FA_OK;
+}
+
 template <typename T>
 int launch(void* out, const void* in, long long M, long long N, long long B, int dim, cudaStream_t st) {
   if (dim == 1) {
     const long long cols = N * B;
+    constexpr long long EPV = 16 / (long long)sizeof(T);
+    const bool vec_ok = M % EPV == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec_ok && cols >= 148) {                       // single-read register-cached form
+      const long long nvec = M / EPV;
+      if (nvec <= 32 * 8) return launch_cached<T, 32>(out, in, M, cols, st);
+      if (nvec <= 256 * 8) return launch_cached<T, 256>(out, in, M, cols, st);
+      if (nvec <= 1024 * 8) return launch_cached<T, 1024>(out, in, M, cols, st);
+    }
     if (cols < 148 * 2 && M >= 4096) {      // few long columns: a block per column
       softmax_dim1_block_kernel<T><<<(unsigned)cols, 1024, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M);
     } else {
