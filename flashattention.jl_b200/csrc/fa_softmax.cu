@@ -2,6 +2,7 @@
 // (rows, strided) of a column-major (M, N, B) array.  Replaces fused_softmax! / col_softmax! /
 // row_softmax! (reference src/fused_softmax.jl:11-39).  HBM-bound: one read + one write when a column fits the
 // registers of its thread group (dim 1, M up to 32768 Float32), two reads + one write otherwise.
+#include <cooperative_groups.h>
 #include "fa_common.cuh"
 
 namespace fa {
@@ -173,6 +174,47 @@ static int launch_cached(void* out, const void* in, long long M, long long cols,
   return FA_OK;
 }
 
+// dim 2, very long rows (N >= 4096): a thread-block CLUSTER of 8 CTAs shares one group of 8 consecutive rows, each CTA
+// takes an eighth of the columns; the per-row (max, sum) partials are exchanged through distributed shared memory, so
+// a row group gets 8 x 256 threads instead of 1024 and the grid fills the GPU (M = 1024: 1024 CTAs instead of 128).  The
+// normalise pass re-reads the CTA's own 8 x N/8 slice, which the resident CTAs keep in L2 (148 SMs x ~0.5 MB).
+template <typename T>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256)
+softmax_dim2_cluster_kernel(T* __restrict__ out, const T* __restrict__ in, long long M, long long N, long long B) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float smx[32][8], ssum[32][8];
+  __shared__ float pmx[8], psum[8];                       // this CTA's partial per row, read by the 7 other CTAs
+  const int rx = threadIdx.x & 7, sy = threadIdx.x >> 3;  // 8 rows x 32 column lanes
+  const unsigned cr = cluster.block_rank();
+  const long long groups = (M + 7) / 8;
+  const long long gb = blockIdx.x / 8;                    // (row group, batch); grid.x = 8 * groups * B
+  const long long b = gb / groups, i = (gb - b * groups) * 8 + rx;
+  const long long Nc = (N + 7) / 8, n0 = cr * Nc, n1 = n0 + Nc < N ? n0 + Nc : N;
+  const bool ok = i < M;
+  const T* x = in + b * M * N + i;
+  T* y = out + b * M * N + i;
+  float mx = -INFINITY, sum = 0.f;
+  if (ok) for (long long n = n0 + sy; n < n1; n += 32) online_merge(mx, sum, to_f32<T>(x[n * M]), 1.f);
+  smx[sy][rx] = mx; ssum[sy][rx] = sum;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float a = -INFINITY, s2 = 0.f;
+    for (int w = 0; w < 32; ++w) online_merge(a, s2, smx[w][threadIdx.x], ssum[w][threadIdx.x]);
+    pmx[threadIdx.x] = a; psum[threadIdx.x] = s2;
+  }
+  cluster.sync();
+  mx = -INFINITY; sum = 0.f;
+  for (unsigned r = 0; r < 8; ++r) {
+    const float* rm = cluster.map_shared_rank(pmx, r);
+    const float* rs = cluster.map_shared_rank(psum, r);
+    online_merge(mx, sum, rm[rx], rs[rx]);
+  }
+  cluster.sync();                                          // nobody leaves while its partials may still be read
+  const float inv = 1.f / sum;
+  if (ok) for (long long n = n0 + sy; n < n1; n += 32) y[n * M] = from_f32<T>(expf(to_f32<T>(x[n * M]) - mx) * inv);
+}
+
 template <typename T>
 int launch(void* out, const void* in, long long M, long long N, long long B, int dim, cudaStream_t st) {
   if (dim == 1) {
@@ -192,6 +234,8 @@ int launch(void* out, const void* in, long long M, long long N, long long B, int
       if (blocks > 148 * 32) blocks = 148 * 32;
       softmax_dim1_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M, cols);
     }
+  } else if (N >= 4096 && ((M + 7) / 8) * B * 8 <= 0x7fffffffLL) {      // very long rows: 8-CTA clusters
+    softmax_dim2_cluster_kernel<T><<<(unsigned)(((M + 7) / 8) * B * 8), 256, 0, st>>>(static_cast<T*>(out), static_cast<const T*>(in), M, N, B);
   } else if (N >= 256) {                    // long strided rows: slice N across the block
     long long blocks = ((M + 7) / 8) * B;
     if (blocks > 148 * 8) blocks = 148 * 8;

@@ -4,10 +4,10 @@
  * the timed CPU baseline of bench.py (`cpu_baseline`, `--impl reference`).  Never linked into or
  * called from the product library.
  *
- * PARITY PINNING STATUS: parity unpinned against the reference binary (no Julia runtime here;
- * src_cpp needs Eigen+MKL+icpc; the reference ships no golden vectors).  Pinned instead against
- * oracle/fa_oracle.py, which is itself pinned against independent implementations
- * (tests/test_oracle.py).
+ * PARITY PINNING STATUS: pinned against oracle/fa_oracle.py (tests/test_c_oracle.py), which since round 2 is itself
+ * pinned to the reference's own src_cpp/FlashAttention.cpp compiled into oracle/_ref (dense forward / backward, 1-D
+ * block attention; tests/test_ref_pin.py).  Parity unpinned for the parts no runnable reference code covers here (no
+ * Julia runtime): NNlib unfold/fold with padding or overlap, circulant -- see the header of fa_oracle.py.
  *
  * What is restated (citations relative to /root/reference):
  *   fa_oracle_dense_fwd      dense_fa!      src/dense.jl:21-102   same task decomposition

@@ -5,10 +5,13 @@ This module is a numpy restatement of the reference's CPU algorithms.  It is the
 ``--impl reference`` legs of ``bench.py`` may import it.  The product path
 (``flashattention.jl_b200/``) never imports anything under ``oracle/``.
 
-PARITY PINNING STATUS: **parity unpinned against the reference binary.**  The
-reference cannot run here (no Julia runtime; ``src_cpp`` needs Eigen+MKL+icpc) and
-ships no golden vectors.  The restatement is therefore
-pinned against *independent* implementations instead (tests/test_oracle.py):
+PARITY PINNING STATUS (round 2): dense forward / backward and 1-D block attention are PINNED to the reference's own
+code -- src_cpp/FlashAttention.cpp (OneDNaive, OneDFast, OneDParallelCPU, OneDNaiveBack, OneDFastBack,
+OneDParallelCPUBack) compiled unmodified into oracle/_ref/libfa_ref_cpp.so (oracle/ref_build/) and compared with
+this module at 1e-12, live and through the frozen vectors tests/golden/ref_cpp_*.npz (tests/test_ref_pin.py).
+**Parity unpinned** for what has no runnable reference code here (no Julia runtime; the reference ships no golden
+vectors): NNlib unfold/fold with padding or overlap (``window``/``unwindow``), the circulant
+storage order and ``fused_softmax``.  Those are pinned against *independent* implementations (tests/test_oracle.py):
   * ``dense_dpa``            vs ``torch.nn.functional.scaled_dot_product_attention``
                              (the analogue of test/test.jl:19 vs NNlib.dot_product_attention)
   * ``window``/``unwindow``  vs ``torch.nn.functional.unfold``/``fold`` (1-D, 2-D) and a
@@ -16,8 +19,9 @@ pinned against *independent* implementations instead (tests/test_oracle.py):
   * ``*_fa``                 vs ``*_dpa``  (test/test.jl:20, bench/compare.jl:20,47,74)
   * ``cartesian_circulant``  vs the closed-form key set  mod(j-1-p+t, N)+1
   * every backward           vs central finite differences in float64
-and the outputs on seeded inputs are frozen in ``tests/golden/`` by
-``tests/golden/make_golden.py``.
+and the outputs on seeded inputs are frozen in ``tests/golden/`` by ``tests/golden/make_golden.py``.  A maintainer
+with Julia can export vectors from the ORIGINAL package (julia/FlashAttention/bench/export_golden.jl) for
+tests/test_julia_golden.py.
 
 Array convention: arrays have the *Julia shapes* of the reference, e.g. ``(N, d, B)`` or
 ``(X, Y, d, B)``, and are handled in Fortran (column-major) order so that linear

@@ -360,3 +360,16 @@ def test_float32_arrays_via_16bit_tensor_cores(via):
     assert fa.last_path() == "tc" and O.dtype == F32
     O0, _, _ = fo.circulant_fa(*(np.asfortranarray(t) for t in (rq, rk, rv)), 65)
     assert rel_err(to_np(O), O0) < RAW_FWD_TOL[via]
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(70, 5000, 2), (8, 4096), (1030, 8200), (256, 65536)])
+def test_fused_softmax_long_rows_cluster_and_cached_columns(shape, dtype):
+    """dims = 2 with N >= 4096 runs the 8-CTA cluster kernel (partial row groups, N not a multiple of 8 or 32); dims = 1
+    on the same arrays runs the register-cached single-read column kernels when a column is a whole number of 16-byte
+    vectors, the two-pass kernels otherwise."""
+    S = randn_np(shape, 3, dtype)
+    for dims in (1, 2):
+        want = fo.fused_softmax(S.astype(np.float64), dims)
+        got = to_np(fa.fused_softmax(to_dev(S, dtype), dims))
+        assert np.abs(got - want).max() < (2e-6 if dtype == F32 else 4e-3) * max(1.0, want.max())
