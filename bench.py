@@ -240,7 +240,7 @@ def main():
         Bc = 512 // world
         cq, ck, cv = (fa.jl_empty((16384, 64, Bc), bf, dev).normal_() for _ in range(3))
         cO = fa.jl_empty((16384, 64, Bc), bf, dev); cl = fa.jl_empty((16384, 1, Bc), torch.float32, dev); cm = fa.jl_empty((16384, 1, Bc), torch.float32, dev)
-        tc_ = timeit(lambda: fa.circulant_fa_(cO, cl, cm, cq, ck, cv, 255), max(args.steps, 10))
+        tc_ = timeit(lambda: fa.circulant_fa_(cO, cl, cm, cq, ck, cv, 255), max(args.steps, 30))     # one pass, 30+ calls
         by = (4 * 16384 * 64 * 2 + 8 * 16384) * Bc
         extra["C4_circulant_fwd"] = {"ms": tc_, "batch_per_gpu": Bc, "tflops_per_gpu": 4.0 * 16384 * 255 * 64 * Bc / tc_ / 1e9,
                                      "alg_gbs_per_gpu": by / tc_ / 1e6, "frac_hbm_peak": by / tc_ / 1e6 / peaks_x["hbm_gbs"],
