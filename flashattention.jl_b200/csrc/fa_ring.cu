@@ -228,7 +228,8 @@ int fa_ring_dense_fwd(const void* q, const void* k, const void* v, void* o, floa
   Geo gd;
   memset(&gd, 0, sizeof(gd));
   gd.mode = MODE_DENSE; gd.d = (int)d; gd.dv = (int)dv; gd.N = Nl; gd.B = B; gd.tau = 1.0f / sqrtf((float)d);
-  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && tc_fwd_supported(gd, dtype);
+  // d = 32 runs on the band kernel, which has no float32-partial output: the ring keeps the exact-fp32 kernels there
+  const bool tc = !(flags & FA_FLAG_FORCE_SIMT) && gd.d != 32 && tc_fwd_supported(gd, dtype);
 
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   RingLanes lanes;

@@ -569,7 +569,8 @@ size_t align256b(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-bool tc_bwd_supported(const Geo& g, int dtype) { return tc_fwd_supported(g, dtype); }
+// the backward kernels are instantiated for d in {64, 128}; d = 32 (forward: band kernel) takes the exact-fp32 backward
+bool tc_bwd_supported(const Geo& g, int dtype) { return (g.d == 64 || g.d == 128) && tc_fwd_supported(g, dtype); }
 
 // workspace: nlse | ndelta | amax[4] | (bf16 inputs, default mode) fp16 re-encodings of q, k, v, dO
 size_t tc_bwd_workspace_bytes(const Geo& g, int dtype, int flags) {

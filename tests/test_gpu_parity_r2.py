@@ -298,6 +298,32 @@ def test_dense_fwd_tc_d32(N, B, dtype):
     assert np.abs(to_np(m) - m0).max() < 2e-3 * max(1.0, np.abs(m0).max())
 
 
+@pytest.mark.parametrize("dtype", [BF16, F16])
+def test_d32_backward_dense_and_circulant(dtype):
+    """d = 32: the forward runs on the tcgen05 band kernel, the dense / circulant BACKWARD kernels exist for d in
+    {64, 128} only and must hand d = 32 to the exact-fp32 kernels (found by tests/test_gpu_fuzz.py: the d = 64
+    instantiation was launched on d = 32 data)."""
+    N, B, W = 304, 3, 37
+    q, k, v, g = (randn_np((N, 32, B), s, dtype) for s in range(4))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    y, l, m = fa.dense_fa(Q, K, V)
+    assert fa.last_path() == "tc"
+    got = fa.dense_fa_backward(Q, K, V, y, G, l, m)
+    assert fa.last_path() == "simt"
+    want = fo.dense_fa_backward_blocked(*f64(q, k, v), to_np(y), g.astype(np.float64), to_np(l), to_np(m))
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < 2e-3
+    q, k, v, g = (randn_np((320, 32, B), s, dtype) for s in range(4))
+    Q, K, V, G = (to_dev(t, dtype) for t in (q, k, v, g))
+    O, l, m = fa.circulant_fa(Q, K, V, W)
+    assert fa.last_path() == "tc"
+    got = fa.circulant_fa_backward(Q, K, V, O, G, l, m, W)
+    assert fa.last_path() == "simt"
+    want = fo.circulant_backward_given(*f64(q, k, v), to_np(O), g.astype(np.float64), to_np(l), to_np(m), W)
+    for a, b_ in zip(got, want):
+        assert rel_err(to_np(a), b_, dtype) < 2e-3
+
+
 @pytest.mark.parametrize("W", [16, 32, 64, 128, 256, 512, 1024])
 def test_circulant_fwd_tc_d32_logged_shapes(W):
     """logs/circ_t16.txt:3-9 (runcirculant, bench/compare.jl:119-129): N = 4096, d = 32, bs = 1, W = 16 .. 1024 (even
