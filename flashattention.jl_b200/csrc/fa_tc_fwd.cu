@@ -628,6 +628,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
         // ping-pong: the exp phase (64 MUFU per thread) of one tile runs while the other tile's warpgroup is in
         // its MUFU-free part (row max, publish, S fetch); the token is a pair of 256-thread named barriers
         if (pp_on) asm volatile("bar.sync %0, 256;" ::"r"(2 + t) : "memory");
+        if ((warp & 3) == 0) TRACE(2 + t, j, 4);          // exp phase entered (token held)
         // ---- P = exp2(s*scale - m) -> 16-bit, written over the first 32 columns of this S buffer.
         // The last EMU elements of every 32 go through the FMA pipe (Cody-Waite split + degree-3
         // minimax polynomial, rel. error 9e-5 << 16-bit P rounding) to unload the MUFU.
@@ -720,12 +721,14 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
           }
 #endif
           tmem_st16(tS + 16 * c, pk);
+          if (c == 0 && (warp & 3) == 0) TRACE(2 + t, j, 6);          // first half of the exps issued
           if (FA_PREFETCH_MID && c == 0 && more && !fetched && mbar_test_wait(nbar, npar)) {
             tc_fence_after();
             tmem_ld32(tS0 + 64 * (bb ^ 1), sn[0]);
             tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);
             fetched = true;
           }
+          if (c == 0 && (warp & 3) == 0) TRACE(2 + t, j, 7);          // mid-phase fetch issued
         }
         }
         if (pp_on) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (t ^ 1)) : "memory");
@@ -736,7 +739,6 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
         if ((warp & 3) == 0) TRACE(2 + t, j, 3);          // P published
         if (more && !fetched) {                // late path: S(j+1) was not ready before the exp phase
           mbar_wait(nbar, npar);
-          if ((warp & 3) == 0) TRACE(2 + t, j, 4);        // S(j+1) available
           tc_fence_after();
           tmem_ld32(tS0 + 64 * (bb ^ 1), sn[0]);
           tmem_ld32(tS0 + 64 * (bb ^ 1) + 32, sn[1]);

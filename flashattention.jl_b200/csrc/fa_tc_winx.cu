@@ -67,6 +67,16 @@ __device__ __forceinline__ void tma_prefetch_5d(const void* tmap, int c0, int c1
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+// y[box] += staged box (element-wise add in L2, 16-bit type of the tensor map); coordinates outside the tensor are dropped
+__device__ __forceinline__ void tma_reduce_add_5d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // NTILES = 4: one CTA per SM, four 128-row tiles = all 512 TMEM columns, 40-byte output runs (config 5: groups of four
 // windows).  NTILES = 2: two CTAs per SM with two tiles each -- smaller boxes and 20-byte runs, but the two CTAs' phases
 // (TMA stream + repack | softmax | output) overlap each other, which one CTA's phases cannot.
@@ -106,6 +116,7 @@ struct XParams {
   unsigned magicNP;            // ceil(2^32 / NP): exact i / NP for i < RG * NP
   long long ngroups;
   float scale_log2;
+  int out_tma;                 // output by ONE TMA reduce-add box per group into a zero-initialised y (FA_WINX_OUT=0: per-thread 4-byte stores)
   int l2_prefetch;             // producer prefetches the next group's boxes into L2 (FA_WINX_PF=0 disables)
   int dbg;                     // FA_TRACE builds: FA_WINX_DBG experiment switch (0 = product behaviour)
   long long* trace;            // FA_TRACE builds: CTA 1 records clock64() per phase of its first 16 groups (20 events each)
@@ -150,6 +161,7 @@ __global__ void __launch_bounds__(XCfg<NTILES>::THREADS, XCfg<NTILES>::CTAS_PER_
 tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_constant__ CUtensorMap tk_s,
                    const __grid_constant__ CUtensorMap tv_s, const __grid_constant__ CUtensorMap tq_l,
                    const __grid_constant__ CUtensorMap tk_l, const __grid_constant__ CUtensorMap tv_l,
+                   const __grid_constant__ CUtensorMap ty_s, const __grid_constant__ CUtensorMap ty_l,
                    const XParams prm) {
   using C = XCfg<NTILES>;
   using T = typename El<FMT>::type;
@@ -172,6 +184,7 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
     fence_barrier_init();
     prefetch_tensormap(&tq_s); prefetch_tensormap(&tk_s); prefetch_tensormap(&tv_s);
     prefetch_tensormap(&tq_l); prefetch_tensormap(&tk_l); prefetch_tensormap(&tv_l);
+    if (prm.out_tma) { prefetch_tensormap(&ty_s); prefetch_tensormap(&ty_l); }
   }
   // static table of a tile row: which (y, z) row of the window and which column of the group's x-range it reads
   if (tid < 128) {
@@ -425,6 +438,52 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
     tc_fence_after();
     XTRACE(11);                                             // O ready
 
+    if (prm.out_tma) {
+      // ---- output by TMA: the group's O rows are staged as ONE box [64 channels][(y, z) row][BX tokens] in the geometry of
+      //      the input boxes (same 16-byte aligned start x0 - shift), zeros in the columns that belong to the neighbouring
+      //      groups, and added to the zero-initialised y by a single cp.reduce.async.bulk.tensor: whole sectors, no store
+      //      instructions, out-of-volume rows / columns dropped by the TMA unit.  (Every token belongs to exactly one window:
+      //      the other groups add +0.)
+      const uint32_t ostg = sbase + C::OFF_TQ;
+      const uint32_t cpitch = pitch * 1u;                     // RG * BX * 2 bytes per channel
+      {
+        const uint32_t nvec = (uint32_t)D * cpitch / 16u;     // BX is a multiple of 8 tokens
+        for (uint32_t i = tid; i < nvec; i += C::CONSUMERS) sts_v4(ostg + 16u * i, 0u, 0u, 0u, 0u);
+      }
+      csync();
+      // TMA stores take no negative start coordinates (tools/probes/tma_reduce_probe.cu: illegal instruction, whereas
+      // coordinates past the upper bound are clipped): the box starts at the clipped origin (xs, ys, zs) and the tokens
+      // are staged relative to it; padding tokens in front of the volume are not staged, the rows / columns the shifted
+      // box gains at its far end stay zero.
+      const int xs = gi.x0 - gi.shift < 0 ? 0 : gi.x0 - gi.shift;       // multiple of 8 tokens
+      const int dy = gi.y0 < 0 ? -gi.y0 : 0, dz = gi.z0 < 0 ? -gi.z0 : 0;
+      {
+        const uint32_t e = valid ? rowtab[row] : 0u;
+        const int rowidx = (int)(e >> 16), kz = rowidx / W, ky = rowidx - kz * W;
+        const int col = gi.x0 + ti * prm.G * W + (int)(e & 0xffffu) - xs;
+        const bool st = valid && col >= 0 && ky >= dy && kz >= dz;
+        const uint32_t o0 = ostg + (uint32_t)((((kz - dz) * W + (ky - dy)) * gi.BX + col) * 2);
+#pragma unroll 1
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + 32 * ch, o);
+          tmem_wait_ld();
+          if (st) {
+#pragma unroll
+            for (int e2 = 0; e2 < 32; ++e2) sts_u16(o0 + (uint32_t)(32 * ch + e2) * cpitch, cvt16<FMT>(__uint_as_float(o[e2]) * inv_l));
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      csync();
+      XTRACE(12);                                             // O staged
+      if (tid == 0) {
+        tma_reduce_add_5d(gi.BX == prm.BXs ? &ty_s : &ty_l, ostg, xs, gi.y0 + dy, gi.z0 + dz, 0, gi.b);
+        bulk_commit();
+        bulk_wait_read0();                                    // the staging (= V and K tiles) may be overwritten
+      }
+    } else {
     // ---- O rows -> 16-bit output staging [channel][(y, z) row][x across the group] over the dead V and K tiles.  Token x
     //      of a row sits at index x - x0 + par (par = x0 & 1; rows start at even global element indices because the x
     //      extent is even), so that a pair of tokens at an even global index is one aligned 32-bit word here.
@@ -493,10 +552,12 @@ tc_winx_fwd_kernel(const __grid_constant__ CUtensorMap tq_s, const __grid_consta
         }
       }
     }
+    }
     csync();              // output staging (= K tiles), row table and TMEM are free for the next group
     XTRACE(13);                                             // runs written
   }
 
+  if (prm.out_tma && tid == 0) bulk_wait0();               // every reduce of this CTA has been performed
   tc_fence_before();
   __syncthreads();                                         // all 17 warps (the producer arrives from its own branch)
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -506,7 +567,7 @@ template <int FMT, int NTILES>
 int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
   using C = XCfg<NTILES>;
   const int dtype = FMT ? FA_BF16 : FA_F16;
-  CUtensorMap tm[6];
+  CUtensorMap tm[8];
   memset(tm, 0, sizeof(tm));
   const void* src[3] = {a.q, a.k, a.v};
   const int by = g.nd >= 2 ? g.W : 1, bz = g.nd >= 3 ? g.W : 1;
@@ -515,6 +576,12 @@ int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
     if ((rc = make_win_tmap_box(&tm[x], src[x], dtype, g, C::D, prm.BXs, by, bz, C::CH))) return rc;
     if ((rc = make_win_tmap_box(&tm[3 + x], src[x], dtype, g, C::D, prm.BXl, by, bz, C::CH))) return rc;
   }
+  if (prm.out_tma) {
+    int rc;
+    if ((rc = make_win_tmap_box(&tm[6], a.o, dtype, g, C::D, prm.BXs, by, bz, C::D))) return rc;
+    if ((rc = make_win_tmap_box(&tm[7], a.o, dtype, g, C::D, prm.BXl, by, bz, C::D))) return rc;
+    FA_CUDA_TRY(cudaMemsetAsync(a.o, 0, (size_t)g.N * C::D * g.B * 2, st));
+  }
   auto kern = tc_winx_fwd_kernel<FMT, NTILES>;
   FA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int dev = 0, sms = 148;
@@ -522,7 +589,7 @@ int launch_winx(const Geo& g, const FwdArgs& a, XParams& prm, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long cap = (long long)sms * C::CTAS_PER_SM;
   const unsigned grid = (unsigned)(prm.ngroups < cap ? prm.ngroups : cap);
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], prm);
   FA_CUDA_TRY(cudaGetLastError());
   return FA_OK;
 }
@@ -572,6 +639,14 @@ int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.trace = nullptr;
   prm.dbg = 0;
   { static const int pf = [] { const char* e = getenv("FA_WINX_PF"); return e ? atoi(e) : 1; }(); prm.l2_prefetch = pf; }
+  {
+    // one TMA reduce-add box per group instead of the 4-byte store loop: needs a 16-byte aligned y, a box of all 64
+    // channels inside the dead V + K tiles and TMA-legal box extents
+    static const int ot = [] { const char* e = getenv("FA_WINX_OUT"); return e ? atoi(e) : 1; }();
+    const int by = g.nd >= 2 ? g.W : 1, bz = g.nd >= 3 ? g.W : 1;
+    const long long box = (long long)prm.BXl * by * bz * 64 * 2;
+    prm.out_tma = ot && NT == 4 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && box <= 2LL * NT * 16384;
+  }
 #ifdef FA_TRACE
   { const char* e = getenv("FA_WINX_DBG"); prm.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("FA_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }

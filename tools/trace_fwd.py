@@ -17,10 +17,14 @@ t = buf.cpu().reshape(4, 64, 8)
 base = int(t[t > 0].min())
 names = {0: "issuer t0", 1: "issuer t1", 2: "softmax t0", 3: "softmax t1"}
 ev = {0: ["pv_wait_start", "pv_p_ready", "qk_wait_start", "qk_k_ready", "qk_issued"],
-      2: ["step_start", "max_done", "exp_st_issued", "p_published", "s_next_avail", "s_next_in_regs"]}
+      2: ["step_start", "max_done", "exp_st_issued", "p_published", "token_held", "s_next_in_regs", "half0_done", "midfetch_issued"]}
 for role in range(4):
     e = ev[0] if role < 2 else ev[2]
     print(names[role], e)
     for s in range(8, 20):
         row = [int(t[role, s, i]) - base if t[role, s, i] > 0 else -1 for i in range(len(e))]
-        print("  step", 32 + s, row, " d_step", int(t[role, s, 0] - t[role, s - 1, 0]))
+        extra = ""
+        if role >= 2:   # softmax: max | wait token | half 0 | mid fetch | half 1 | publish | tail
+            r = row
+            extra = f"  max {r[1]-r[0]} token_wait {r[4]-r[1]} half0 {r[6]-r[4]} midfetch {r[7]-r[6]} half1 {r[2]-r[7]} publish {r[3]-r[2]} regs {r[5]-r[3]}"
+        print("  step", 32 + s, row, " d_step", int(t[role, s, 0] - t[role, s - 1, 0]), extra)
