@@ -640,9 +640,11 @@ int tc_winx_fwd(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.dbg = 0;
   { static const int pf = [] { const char* e = getenv("FA_WINX_PF"); return e ? atoi(e) : 1; }(); prm.l2_prefetch = pf; }
   {
-    // one TMA reduce-add box per group instead of the 4-byte store loop: needs a 16-byte aligned y, a box of all 64
-    // channels inside the dead V + K tiles and TMA-legal box extents
-    static const int ot = [] { const char* e = getenv("FA_WINX_OUT"); return e ? atoi(e) : 1; }();
+    // FA_WINX_OUT=1: one TMA reduce-add box per group instead of the 4-byte store loop (needs a 16-byte aligned y and a box
+    // of all 64 channels inside the dead V + K tiles).  Measured (profiles/r2f_winx.md): the output phase of a group drops
+    // from 10 000 to 5 200 clk, but the zero-fill pass over y and the reduction's sector fills cost more at config 5, B = 64
+    // (7.77 vs 6.58 ms); one 256^3 volume gains 5 % (4.44 vs 4.66 ms).  Off by default.
+    static const int ot = [] { const char* e = getenv("FA_WINX_OUT"); return e ? atoi(e) : 0; }();
     const int by = g.nd >= 2 ? g.W : 1, bz = g.nd >= 3 ? g.W : 1;
     const long long box = (long long)prm.BXl * by * bz * 64 * 2;
     prm.out_tma = ot && NT == 4 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && box <= 2LL * NT * 16384;
