@@ -128,7 +128,8 @@ struct TcParams {
   float scale_log2;      // tau * log2(e)
   int o_f32;             // store O as float32
   int stagger;           // clocks by which the softmax warpgroup of Q tile 1 starts late (experiment)
-  int pingpong;          // the two softmax warpgroups take turns on the MUFU-heavy exp phase (named barriers)
+  int pingpong;          // the two softmax warpgroups take turns on the MUFU-heavy exp phase (named barriers): 1 = on the
+                         // whole phase, 2 = on its first half only (the second half overlaps the other tile's first half)
   long long* trace;      // FA_TRACE builds: CTA (0,0) records (clock) per (role, step, event); else NULL
 };
 
@@ -729,9 +730,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ C
             fetched = true;
           }
           if (c == 0 && (warp & 3) == 0) TRACE(2 + t, j, 7);          // mid-phase fetch issued
+          // soft token (pingpong = 2): hand over after the first half, so that the second half of this tile and the first
+          // half of the other one share the MUFU pipe (two warps per scheduler reach the pipe rate, a lone warp does not)
+          if (c == 0 && pp_on && prm.pingpong == 2) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (t ^ 1)) : "memory");
         }
         }
-        if (pp_on) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (t ^ 1)) : "memory");
+        if (pp_on && prm.pingpong != 2) asm volatile("bar.arrive %0, 256;" ::"r"(2 + (t ^ 1)) : "memory");
         if ((warp & 3) == 0) TRACE(2 + t, j, 2);          // exps + pack + st issued
         tmem_wait_st();
         tc_fence_before();
@@ -899,8 +903,10 @@ int launch_tc(const Geo& g, const FwdArgs& a, int dtype, cudaStream_t st) {
   prm.o_f32 = a.o_f32;
   static const int stagger = [] { const char* e = getenv("FA_FWD_STAGGER"); return e ? atoi(e) : 0; }();
   prm.stagger = stagger;
-  // default on: 1.826 vs 1.860 ms at N=8192, d=128, B=64 (same box, three interleaved runs); FA_FWD_PINGPONG=0 disables
-  static const int pingpong = [] { const char* e = getenv("FA_FWD_PINGPONG"); return e ? atoi(e) : 1; }();
+  // 1 = the token covers the whole exp phase: 1.826 vs 1.860 ms at N=8192, d=128, B=64 (same box, three interleaved runs);
+  // 2 (default) = handed over after the first half: 1.752 vs 1.815 ms (profiles/r2x_dense_fwd_experiments.md);
+  // FA_FWD_PINGPONG=0 disables
+  static const int pingpong = [] { const char* e = getenv("FA_FWD_PINGPONG"); return e ? atoi(e) : 2; }();
   prm.pingpong = pingpong;
   prm.trace = nullptr;
 #ifdef FA_TRACE

@@ -258,6 +258,16 @@ def test_windowed_streamed_kernel_forced():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_windowed_streamed_kernel_tma_reduce_output():
+    """The same geometries with the opt-in output path FA_WINX_OUT=1: one cp.reduce.async.bulk.tensor (.add) box per group
+    into a zero-initialised y, box origin clipped to the volume (TMA stores take no negative start coordinates)."""
+    import os, subprocess, sys
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "check_winx.py")
+    r = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, FA_WINX="1", FA_WINX_OUT="1"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_windowed_streamed_kernel_default_dispatch_config5_batch():
     """config 5 at batch 4 (43904 windows = 10976 groups >= 4 per SM): the default dispatch takes the streamed kernel;
     sampled windows against the oracle evaluated on those windows only (the full oracle at B = 4 is slow)."""
