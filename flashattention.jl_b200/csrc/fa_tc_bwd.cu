@@ -93,6 +93,7 @@ struct BwdParams {
   int X, Y;              // 2-D periodic neighbourhood (mode circulant, X > 0): image extents, N = X * Y, x fastest
   float scale_log2;      // tau * log2(e)
   float tau;
+  int dbg;               // FA_TRACE builds: timing knock-outs with WRONG results (1 = half the ex2, 2 = half the T MMAs, 4 = half the accumulating MMAs)
 };
 
 __host__ __device__ inline int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -310,12 +311,18 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
+#ifdef FA_TRACE
+            if ((prm.dbg & 2) && ks >= D / 32) continue;
+#endif
             if (C::OWN_TMEM) mma_ts(tT1 + 64 * bb, tmem_base + C::COL_X + ks * 8, y1 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
             else mma_ss(tT1 + 64 * bb, x1d + (uint64_t)(ks * 128), y1 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
           }
           tc_commit(bar(C::BAR_T1 + bb));
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
+#ifdef FA_TRACE
+            if ((prm.dbg & 2) && ks >= D / 32) continue;
+#endif
             if (C::OWN_TMEM) mma_ts(tT2 + 64 * bb, tmem_base + C::COL_X + D / 2 + ks * 8, y2 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
             else mma_ss(tT2 + 64 * bb, x2d + (uint64_t)(ks * 128), y2 + (uint64_t)(ks * 128), idesc_t, ks > 0 ? 1u : 0u);
           }
@@ -335,8 +342,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < BT / 16; ++ks)
+            for (int ks = 0; ks < BT / 16; ++ks) {
+#ifdef FA_TRACE
+              if ((prm.dbg & 4) && ks >= BT / 32) continue;
+#endif
               mma_ts(tA0, tT1 + 64 * bb + ks * 8, y2 + (uint64_t)(ks * 2), idesc_acc, (j > 0 || ks > 0) ? 1u : 0u);
+            }
           }
           __syncwarp();
         }
@@ -344,8 +355,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BT / 16; ++ks)
+          for (int ks = 0; ks < BT / 16; ++ks) {
+#ifdef FA_TRACE
+            if ((prm.dbg & 4) && ks >= BT / 32) continue;
+#endif
             mma_ts(KIND == 0 ? tA1 : tA0, tT2 + 64 * bb + ks * 8, y1 + (uint64_t)(ks * 2), idesc_acc, (j > 0 || ks > 0) ? 1u : 0u);
+          }
           tc_commit(bar(C::BAR_EMPTY + s));
         }
         __syncwarp();
@@ -461,7 +476,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ 
           }
           const float2 xa = __ffma2_rn(make_float2(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])), scale2, make_float2(nl4.x, nl4.y));
           const float2 xb = __ffma2_rn(make_float2(__uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3])), scale2, make_float2(nl4.z, nl4.w));
+#ifdef FA_TRACE
+          const bool noex = (prm.dbg & 1) && c == 1;
+          const float2 pa = noex ? xa : make_float2(ex2(xa.x), ex2(xa.y)), pb = noex ? xb : make_float2(ex2(xb.x), ex2(xb.y));
+#else
           const float2 pa = make_float2(ex2(xa.x), ex2(xa.y)), pb = make_float2(ex2(xb.x), ex2(xb.y));
+#endif
           const float2 ta = __fadd2_rn(make_float2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), make_float2(nd4.x, nd4.y));
           const float2 tb = __fadd2_rn(make_float2(__uint_as_float(dp[e + 2]), __uint_as_float(dp[e + 3])), make_float2(nd4.z, nd4.w));
           const float2 da = __fmul2_rn(pa, ta), db = __fmul2_rn(pb, tb);
@@ -542,6 +562,10 @@ int launch_tc_bwd(const Geo& g, const BwdArgs& a, const void* q, const void* k, 
   const bool td = g.mode == MODE_CIRCULANT && g.nd == 2;
   prm.X = td ? g.s[0] : 0; prm.Y = td ? g.s[1] : 0;
   prm.scale_log2 = g.tau * LOG2E; prm.tau = g.tau;
+  prm.dbg = 0;
+#ifdef FA_TRACE
+  { const char* e = getenv("FA_BWD_DBG"); prm.dbg = e ? atoi(e) : 0; }
+#endif
   const dim3 grid(td ? (unsigned)(((g.s[0] + 127) / 128) * g.s[1]) : (unsigned)((g.N + 127) / 128), (unsigned)g.B);
   {
     auto kern = tc_bwd_kernel<D, FMT, 0, OBF, 0>;
